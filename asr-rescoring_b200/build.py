@@ -1,0 +1,73 @@
+"""In-tree build of libpllb200.so with nvcc for sm_100a (no GPU needed to compile)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpllb200.so")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+          "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# translation unit -> extra flags
+UNITS = {
+    "api.cu": [],
+    "gemm_tcgen05.cu": [],
+    "encoder_kernels.cu": [],
+    # fp64 combiner must round like numpy: no FMA contraction, IEEE division
+    "rescore_kernels.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
+}
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pllb.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = []
+    procs = []
+    for src, extra in UNITS.items():
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, cmd, p in procs:
+        out, _ = p.communicate()
+        log.append(f"$ {' '.join(cmd)}\n{out}")
+        if p.returncode != 0:
+            sys.stderr.write(log[-1])
+            raise RuntimeError(f"nvcc failed on {src}")
+    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log.append(f"$ {' '.join(cmd)}\n{out.stdout}")
+    if out.returncode != 0:
+        sys.stderr.write(log[-1])
+        raise RuntimeError("link failed")
+    with open(os.path.join(objdir, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,681 @@
+// api.cu — the C ABI of libpllb200.so (include/pllb.h): handle, weight conversion,
+// chunked PLL scoring pipeline, host-buffer wrappers and parity/debug hooks.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+
+namespace pllb {
+
+static thread_local std::string g_last_error;
+thread_local int64_t g_launch_counter = 0;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace pllb
+
+using namespace pllb;
+
+namespace {
+
+enum GemmKind { G_QKV = 0, G_AO, G_FF1, G_FF2, G_HEAD, G_DEC, G_KINDS };
+
+struct LayerDev {
+  __nv_bfloat16 *qkv_w, *ao_w, *ff1_w, *ff2_w;
+  float *qkv_b, *ao_b, *ao_g, *ao_be, *ff1_b, *ff2_b, *out_g, *out_be;
+};
+
+struct TimedLaunch {
+  cudaEvent_t start, stop;
+  int kind;
+};
+
+}  // namespace
+
+struct pllb_context {
+  pllb_model_desc d{};
+  int device = 0;
+  int64_t cap_rows = 0, cap_copies = 0, cap_hyps = 0;
+  int vocab_pad = 0, tiles_v = 0;
+  std::vector<void*> owned;          // every cudaMalloc of this handle
+  int64_t owned_bytes = 0;
+  // parameters
+  float *word_emb = nullptr, *pos_emb = nullptr, *type_emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+  std::vector<LayerDev> layers;
+  __nv_bfloat16 *head_w = nullptr, *dec_w = nullptr;
+  float *head_b = nullptr, *head_g = nullptr, *head_be = nullptr, *dec_b = nullptr;
+  // activations of one chunk
+  float *hidden_f32 = nullptr, *y_f32 = nullptr;
+  __nv_bfloat16 *hidden_bf16 = nullptr, *wide = nullptr /* qkv [rows,3H] or ffn [rows,I] */, *ctx = nullptr;
+  CopyPlan plan{};
+  __nv_bfloat16 *hg = nullptr, *t_bf16 = nullptr;
+  float *t_f32 = nullptr, *label_logit = nullptr, *tok_logp = nullptr;
+  float2* partials = nullptr;
+  // per-call hypothesis metadata (grown on demand)
+  int32_t* meta_dev = nullptr;
+  int32_t* meta_host = nullptr;     // pinned
+  int64_t meta_cap = 0;
+  // scratch for the _host entry points
+  void* io_dev = nullptr;
+  int64_t io_cap = 0;
+  // stats / timing
+  pllb_stats stats{};
+  bool timing = false;
+  std::vector<TimedLaunch> timed;
+  size_t timed_used = 0;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  bool have_total = false;
+  float gemm_ms_kind[G_KINDS] = {0};
+  double gemm_flops_kind[G_KINDS] = {0};
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(pllb_context* c, T** out, int64_t count) {
+  void* p = nullptr;
+  const int64_t bytes = std::max<int64_t>(count, 1) * (int64_t)sizeof(T);
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(PLLB_ERR_OOM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(e));
+  }
+  c->owned.push_back(p);
+  c->owned_bytes += bytes;
+  *out = reinterpret_cast<T*>(p);
+  return PLLB_OK;
+}
+
+int copy_f32(pllb_context* c, float** dst, const float* src, int64_t n, cudaStream_t s) {
+  int rc = dev_alloc(c, dst, n);
+  if (rc) return rc;
+  PLLB_CUDA(cudaMemcpyAsync(*dst, src, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  return PLLB_OK;
+}
+
+int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n, cudaStream_t s) {
+  int rc = dev_alloc(c, dst, n);
+  if (rc) return rc;
+  return launch_f32_to_bf16(src, *dst, n, s);
+}
+
+#define RC(expr)            \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const float* bias, void* C, int64_t M, int N,
+               int K, int epi, const LseArgs* lse, cudaStream_t s) {
+  TimedLaunch* tl = nullptr;
+  if (c->timing) {
+    if (c->timed_used == c->timed.size()) {
+      TimedLaunch t{};
+      PLLB_CUDA(cudaEventCreate(&t.start));
+      PLLB_CUDA(cudaEventCreate(&t.stop));
+      c->timed.push_back(t);
+    }
+    tl = &c->timed[c->timed_used++];
+    tl->kind = kind;
+    PLLB_CUDA(cudaEventRecord(tl->start, s));
+  }
+  RC(launch_gemm_tcgen05(A, W, bias, C, M, N, K, epi, lse, s));
+  if (tl) PLLB_CUDA(cudaEventRecord(tl->stop, s));
+  const double fl = 2.0 * (double)M * (double)N * (double)K;
+  c->stats.gemm_flops += fl;
+  c->gemm_flops_kind[kind] += fl;
+  c->stats.last_gemm_launches += 1;
+  return PLLB_OK;
+}
+
+// Encoder + head over one chunk whose metadata (tok_off / copy_base / row_base, each
+// n_hyp+1 int32) already sits in device memory.  upto_layer < 0: full scoring.
+int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, const int32_t* copy_base,
+              const int32_t* row_base, int32_t n_hyp, int32_t n_copies, int64_t n_rows, int max_T, double* out_pll,
+              float* out_tok_logp, int upto_layer, cudaStream_t s) {
+  const pllb_model_desc& d = c->d;
+  const int H = d.hidden, I = d.intermediate;
+  RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, c->plan, s));
+  RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
+                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->hidden_f32, c->hidden_bf16, s));
+  const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
+  for (int l = 0; l < n_layers; ++l) {
+    const LayerDev& L = c->layers[l];
+    RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide, n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
+    RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, s));
+    RC(timed_gemm(c, G_AO, c->ctx, L.ao_w, L.ao_b, c->y_f32, n_rows, H, H, EPI_BIAS_F32, nullptr, s));
+    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.ao_g, L.ao_be, d.ln_eps, n_rows, H, s));
+    RC(timed_gemm(c, G_FF1, c->hidden_bf16, L.ff1_w, L.ff1_b, c->wide, n_rows, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
+    RC(timed_gemm(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, c->y_f32, n_rows, H, I, EPI_BIAS_F32, nullptr, s));
+    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.out_g, L.out_be, d.ln_eps, n_rows, H, s));
+  }
+  if (upto_layer >= 0) return PLLB_OK;
+  // MLM head at the masked row of every copy only (the reference evaluates all B*T rows,
+  // transformers modeling_bert.py:975, and keeps one: MLM_PLL/main.py:101).
+  RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->hg, s));
+  RC(timed_gemm(c, G_HEAD, c->hg, c->head_w, c->head_b, c->t_f32, n_copies, H, H, EPI_BIAS_GELU_F32, nullptr, s));
+  RC(launch_plain_ln_bf16(c->t_f32, c->t_bf16, c->head_g, c->head_be, d.ln_eps, n_copies, H, s));
+  LseArgs lse{c->plan.label, c->partials, c->label_logit, d.vocab};
+  RC(timed_gemm(c, G_DEC, c->t_bf16, c->dec_w, c->dec_b, nullptr, n_copies, c->vocab_pad, H, EPI_LSE, &lse, s));
+  RC(launch_lse_finish(c->partials, c->label_logit, n_copies, c->tiles_v, c->tok_logp, s));
+  RC(launch_hyp_sum(c->tok_logp, copy_base, n_hyp, out_pll, out_tok_logp, s));
+  return PLLB_OK;
+}
+
+struct Chunk {
+  int32_t hyp_begin, n_hyp, n_copies;
+  int64_t n_rows, tok_begin;
+  int max_T;
+  int64_t meta_off;   // offset (in int32) of this chunk's metadata block
+};
+
+int ensure_meta(pllb_context* c, int64_t need, cudaStream_t s) {
+  if (need <= c->meta_cap) return PLLB_OK;
+  PLLB_CUDA(cudaStreamSynchronize(s));
+  PLLB_CUDA(cudaDeviceSynchronize());
+  if (c->meta_dev) cudaFree(c->meta_dev);
+  if (c->meta_host) cudaFreeHost(c->meta_host);
+  c->meta_dev = nullptr;
+  c->meta_host = nullptr;
+  const int64_t cap = need + need / 2 + 1024;
+  PLLB_CUDA(cudaMalloc(&c->meta_dev, sizeof(int32_t) * cap));
+  PLLB_CUDA(cudaHostAlloc(&c->meta_host, sizeof(int32_t) * cap, cudaHostAllocDefault));
+  c->meta_cap = cap;
+  return PLLB_OK;
+}
+
+// Plans chunks on the host (offsets are control metadata), uploads the metadata once and
+// enqueues every chunk on `s` without synchronising.
+int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, int32_t n_hyp, double* out_pll,
+               float* out_tok_logp, int upto_layer, float* out_hidden, cudaStream_t s) {
+  if (!c) return fail(PLLB_ERR_INVALID, "null handle");
+  if (n_hyp < 0 || (n_hyp > 0 && (!off || !hyp_tokens && off[n_hyp] > off[0])))
+    return fail(PLLB_ERR_INVALID, "pllb_score: null argument");
+  PLLB_CUDA(cudaSetDevice(c->device));
+  const int64_t launches_before = g_launch_counter;
+  c->stats.last_gemm_launches = 0;
+  c->timed_used = 0;
+  std::vector<Chunk> chunks;
+  {
+    Chunk cur{0, 0, 0, 0, n_hyp > 0 ? off[0] : 0, 0, 0};
+    for (int32_t h = 0; h < n_hyp; ++h) {
+      const int64_t L = off[h + 1] - off[h];
+      if (L < 0) return fail(PLLB_ERR_INVALID, "pllb_score: offsets not monotone");
+      if (L + 2 > c->d.max_position)
+        return fail(PLLB_ERR_TOO_LONG, "hypothesis " + std::to_string(h) + " has " + std::to_string(L) +
+                                           " tokens; max_position_embeddings allows " + std::to_string(c->d.max_position - 2));
+      const int64_t rows = L * (L + 2);
+      if (rows > c->cap_rows || L > c->cap_copies)
+        return fail(PLLB_ERR_OOM, "a single hypothesis exceeds max_chunk_tokens");
+      if (cur.n_hyp > 0 && (cur.n_rows + rows > c->cap_rows || cur.n_copies + L > c->cap_copies || cur.n_hyp + 1 > c->cap_hyps)) {
+        chunks.push_back(cur);
+        cur = Chunk{h, 0, 0, 0, off[h], 0, 0};
+      }
+      cur.n_hyp += 1;
+      cur.n_copies += (int32_t)L;
+      cur.n_rows += rows;
+      cur.max_T = std::max(cur.max_T, (int)L + 2);
+    }
+    if (cur.n_hyp > 0) chunks.push_back(cur);
+  }
+  if (upto_layer >= 0 && chunks.size() > 1) return fail(PLLB_ERR_OOM, "pllb_debug_hidden: input must fit one chunk");
+  int64_t meta_need = 0;
+  for (auto& ch : chunks) {
+    ch.meta_off = meta_need;
+    meta_need += 3 * (int64_t)(ch.n_hyp + 1);
+  }
+  RC(ensure_meta(c, meta_need, s));
+  for (const auto& ch : chunks) {
+    int32_t* tok_off = c->meta_host + ch.meta_off;
+    int32_t* copy_base = tok_off + (ch.n_hyp + 1);
+    int32_t* row_base = copy_base + (ch.n_hyp + 1);
+    int64_t t = 0, cb = 0, rb = 0;
+    for (int32_t i = 0; i <= ch.n_hyp; ++i) {
+      tok_off[i] = (int32_t)t; copy_base[i] = (int32_t)cb; row_base[i] = (int32_t)rb;
+      if (i < ch.n_hyp) {
+        const int64_t L = off[ch.hyp_begin + i + 1] - off[ch.hyp_begin + i];
+        t += L; cb += L; rb += L * (L + 2);
+      }
+    }
+  }
+  if (meta_need > 0)
+    PLLB_CUDA(cudaMemcpyAsync(c->meta_dev, c->meta_host, sizeof(int32_t) * meta_need, cudaMemcpyHostToDevice, s));
+  if (c->timing) {
+    if (!c->ev_begin) { PLLB_CUDA(cudaEventCreate(&c->ev_begin)); PLLB_CUDA(cudaEventCreate(&c->ev_end)); }
+    PLLB_CUDA(cudaEventRecord(c->ev_begin, s));
+  }
+  for (const auto& ch : chunks) {
+    const int32_t* tok_off = c->meta_dev + ch.meta_off;
+    const int32_t* copy_base = tok_off + (ch.n_hyp + 1);
+    const int32_t* row_base = copy_base + (ch.n_hyp + 1);
+    RC(run_chunk(c, hyp_tokens + (ch.tok_begin - off[0]), tok_off, copy_base, row_base, ch.n_hyp, ch.n_copies, ch.n_rows,
+                 ch.max_T, out_pll ? out_pll + ch.hyp_begin : nullptr,
+                 out_tok_logp ? out_tok_logp + (ch.tok_begin - off[0]) : nullptr, upto_layer, s));
+    if (out_hidden)
+      PLLB_CUDA(cudaMemcpyAsync(out_hidden, c->hidden_f32, sizeof(float) * ch.n_rows * c->d.hidden,
+                                cudaMemcpyDeviceToDevice, s));
+    c->stats.chunks += 1;
+    c->stats.hyps_scored += ch.n_hyp;
+    c->stats.copies_scored += ch.n_copies;
+    c->stats.tokens_expanded += ch.n_rows;
+  }
+  if (c->timing) { PLLB_CUDA(cudaEventRecord(c->ev_end, s)); c->have_total = true; }
+  c->stats.kernel_launches += g_launch_counter - launches_before;
+  return PLLB_OK;
+}
+
+int ensure_io(pllb_context* c, int64_t bytes) {
+  if (bytes <= c->io_cap) return PLLB_OK;
+  PLLB_CUDA(cudaDeviceSynchronize());
+  if (c->io_dev) cudaFree(c->io_dev);
+  c->io_dev = nullptr;
+  PLLB_CUDA(cudaMalloc(&c->io_dev, (size_t)(bytes + bytes / 4 + 4096)));
+  c->io_cap = bytes + bytes / 4 + 4096;
+  return PLLB_OK;
+}
+
+int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(PLLB_ERR_NO_DEVICE, "no CUDA device visible; libpllb200 has no CPU fallback");
+  }
+  return PLLB_OK;
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" {
+
+const char* pllb_last_error(void) { return g_last_error.c_str(); }
+int pllb_abi_version(void) { return PLLB_ABI_VERSION; }
+
+int pllb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weights* w, int64_t max_chunk_tokens,
+                int device) {
+  if (!out || !desc || !w || !w->layers) return fail(PLLB_ERR_INVALID, "pllb_create: null argument");
+  *out = nullptr;
+  RC(check_device());
+  const pllb_model_desc& d = *desc;
+  if (d.hidden % 256 != 0 || d.hidden < 256 || d.hidden > 1024 || d.num_heads * 64 != d.hidden ||
+      d.intermediate % 256 != 0 || d.num_layers < 0 || d.vocab < 1 || d.max_position < 3)
+    return fail(PLLB_ERR_INVALID, "unsupported model shape: need hidden in {256,512,768,1024}, head dim 64, "
+                                  "intermediate % 256 == 0");
+  PLLB_CUDA(cudaSetDevice(device));
+  int major = 0;
+  PLLB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail(PLLB_ERR_NO_DEVICE, "device is not sm_100 (B200); libpllb200 has no other code path");
+  pllb_context* c = new pllb_context();
+  c->d = d;
+  c->device = device;
+  cudaStream_t s = 0;
+  const int H = d.hidden, I = d.intermediate, V = d.vocab;
+  int rc = PLLB_OK;
+  auto bail = [&](int code) {
+    pllb_destroy(c);
+    return code;
+  };
+#define TRY(expr)                  \
+  do {                             \
+    rc = (expr);                   \
+    if (rc) return bail(rc);       \
+  } while (0)
+  TRY(copy_f32(c, &c->word_emb, w->word_emb, (int64_t)V * H, s));
+  TRY(copy_f32(c, &c->pos_emb, w->pos_emb, (int64_t)d.max_position * H, s));
+  TRY(copy_f32(c, &c->type_emb, w->type_emb, H, s));   // token_type 0 only (MLM_PLL/main.py:89-94 passes none)
+  TRY(copy_f32(c, &c->emb_g, w->emb_ln_g, H, s));
+  TRY(copy_f32(c, &c->emb_b, w->emb_ln_b, H, s));
+  c->layers.resize(d.num_layers);
+  for (int l = 0; l < d.num_layers; ++l) {
+    const pllb_layer_weights& lw = w->layers[l];
+    LayerDev& L = c->layers[l];
+    TRY(dev_alloc(c, &L.qkv_w, (int64_t)3 * H * H));
+    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, s));
+    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, s));
+    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, s));
+    TRY(dev_alloc(c, &L.qkv_b, 3 * H));
+    cudaMemcpyAsync(L.qkv_b, lw.q_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(L.qkv_b + H, lw.k_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(L.qkv_b + 2 * H, lw.v_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
+    TRY(conv_bf16(c, &L.ao_w, lw.ao_w, (int64_t)H * H, s));
+    TRY(copy_f32(c, &L.ao_b, lw.ao_b, H, s));
+    TRY(copy_f32(c, &L.ao_g, lw.ao_ln_g, H, s));
+    TRY(copy_f32(c, &L.ao_be, lw.ao_ln_b, H, s));
+    TRY(conv_bf16(c, &L.ff1_w, lw.ff1_w, (int64_t)I * H, s));
+    TRY(copy_f32(c, &L.ff1_b, lw.ff1_b, I, s));
+    TRY(conv_bf16(c, &L.ff2_w, lw.ff2_w, (int64_t)H * I, s));
+    TRY(copy_f32(c, &L.ff2_b, lw.ff2_b, H, s));
+    TRY(copy_f32(c, &L.out_g, lw.out_ln_g, H, s));
+    TRY(copy_f32(c, &L.out_be, lw.out_ln_b, H, s));
+  }
+  TRY(conv_bf16(c, &c->head_w, w->head_w, (int64_t)H * H, s));
+  TRY(copy_f32(c, &c->head_b, w->head_b, H, s));
+  TRY(copy_f32(c, &c->head_g, w->head_ln_g, H, s));
+  TRY(copy_f32(c, &c->head_be, w->head_ln_b, H, s));
+  c->vocab_pad = (int)align_up(V, 256);
+  c->tiles_v = c->vocab_pad / 256;
+  TRY(dev_alloc(c, &c->dec_w, (int64_t)c->vocab_pad * H));
+  cudaMemsetAsync(c->dec_w, 0, sizeof(__nv_bfloat16) * (size_t)c->vocab_pad * H, s);
+  TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, s));
+  TRY(dev_alloc(c, &c->dec_b, c->vocab_pad));
+  cudaMemsetAsync(c->dec_b, 0, sizeof(float) * c->vocab_pad, s);
+  cudaMemcpyAsync(c->dec_b, w->decoder_b, sizeof(float) * V, cudaMemcpyDeviceToDevice, s);
+
+  // workspace: sized by the expanded-token budget of one chunk
+  if (max_chunk_tokens <= 0) max_chunk_tokens = (int64_t)1 << 20;
+  const int64_t longest = (int64_t)(d.max_position - 2) * d.max_position;   // one max-length hypothesis
+  (void)longest;
+  c->cap_rows = align_up(std::max<int64_t>(max_chunk_tokens, 1024), 128);
+  c->cap_copies = c->cap_rows / 4 + 128;
+  c->cap_hyps = c->cap_rows / 4 + 128;
+  const int64_t R = c->cap_rows, C = c->cap_copies;
+  const int wide = std::max(3 * H, I);
+  TRY(dev_alloc(c, &c->hidden_f32, R * H));
+  TRY(dev_alloc(c, &c->hidden_bf16, R * H));
+  TRY(dev_alloc(c, &c->wide, R * wide));
+  TRY(dev_alloc(c, &c->ctx, R * H));
+  TRY(dev_alloc(c, &c->y_f32, R * H));
+  TRY(dev_alloc(c, &c->plan.seq_start, C));
+  TRY(dev_alloc(c, &c->plan.seq_len, C));
+  TRY(dev_alloc(c, &c->plan.mask_row, C));
+  TRY(dev_alloc(c, &c->plan.label, C));
+  TRY(dev_alloc(c, &c->plan.hyp, C));
+  TRY(dev_alloc(c, &c->hg, C * H));
+  TRY(dev_alloc(c, &c->t_f32, C * H));
+  TRY(dev_alloc(c, &c->t_bf16, C * H));
+  TRY(dev_alloc(c, &c->partials, C * c->tiles_v));
+  TRY(dev_alloc(c, &c->label_logit, C));
+  TRY(dev_alloc(c, &c->tok_logp, C));
+#undef TRY
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    pllb_destroy(c);
+    return fail(PLLB_ERR_CUDA, std::string("pllb_create: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return PLLB_OK;
+}
+
+int pllb_destroy(pllb_handle h) {
+  if (!h) return PLLB_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->owned) cudaFree(p);
+  if (h->meta_dev) cudaFree(h->meta_dev);
+  if (h->meta_host) cudaFreeHost(h->meta_host);
+  if (h->io_dev) cudaFree(h->io_dev);
+  for (auto& t : h->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+  if (h->ev_begin) { cudaEventDestroy(h->ev_begin); cudaEventDestroy(h->ev_end); }
+  delete h;
+  return PLLB_OK;
+}
+
+int64_t pllb_workspace_bytes(pllb_handle h) { return h ? h->owned_bytes : 0; }
+
+int pllb_score(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets, int32_t n_hyp, double* out_pll,
+               float* out_token_logp, void* stream) {
+  if (!out_pll && n_hyp > 0) return fail(PLLB_ERR_INVALID, "pllb_score: out_pll is null");
+  if (n_hyp > 0 && !hyp_offsets) return fail(PLLB_ERR_INVALID, "pllb_score: hyp_offsets is null");
+  const int64_t o0 = n_hyp > 0 ? hyp_offsets[0] : 0;   // tokens / token_logp are indexed by absolute offset
+  return score_impl(h, hyp_tokens ? hyp_tokens + o0 : nullptr, hyp_offsets, n_hyp, out_pll,
+                    out_token_logp ? out_token_logp + o0 : nullptr, -1, nullptr, (cudaStream_t)stream);
+}
+
+int pllb_score_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, int32_t n_hyp, double* out_pll,
+                    float* out_token_logp) {
+  if (!h) return fail(PLLB_ERR_INVALID, "null handle");
+  if (n_hyp <= 0) return PLLB_OK;
+  if (!off || !out_pll) return fail(PLLB_ERR_INVALID, "pllb_score_host: null argument");
+  PLLB_CUDA(cudaSetDevice(h->device));
+  const int64_t n_tok = off[n_hyp] - off[0];
+  const int64_t b_tok = align_up(sizeof(int32_t) * std::max<int64_t>(n_tok, 1), 256);
+  const int64_t b_pll = align_up(sizeof(double) * n_hyp, 256);
+  const int64_t b_lp = align_up(sizeof(float) * std::max<int64_t>(n_tok, 1), 256);
+  RC(ensure_io(h, b_tok + b_pll + b_lp));
+  uint8_t* base = reinterpret_cast<uint8_t*>(h->io_dev);
+  int32_t* d_tok = reinterpret_cast<int32_t*>(base);
+  double* d_pll = reinterpret_cast<double*>(base + b_tok);
+  float* d_lp = reinterpret_cast<float*>(base + b_tok + b_pll);
+  cudaStream_t s = 0;
+  if (n_tok > 0)
+    PLLB_CUDA(cudaMemcpyAsync(d_tok, hyp_tokens + off[0], sizeof(int32_t) * n_tok, cudaMemcpyHostToDevice, s));
+  RC(score_impl(h, d_tok, off, n_hyp, d_pll, out_token_logp ? d_lp : nullptr, -1, nullptr, s));
+  PLLB_CUDA(cudaMemcpyAsync(out_pll, d_pll, sizeof(double) * n_hyp, cudaMemcpyDeviceToHost, s));
+  if (out_token_logp && n_tok > 0)
+    PLLB_CUDA(cudaMemcpyAsync(out_token_logp + off[0], d_lp, sizeof(float) * n_tok, cudaMemcpyDeviceToHost, s));
+  PLLB_CUDA(cudaStreamSynchronize(s));
+  return PLLB_OK;
+}
+
+int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, int32_t n_hyp, int32_t* out_ids,
+                int32_t* out_mask_pos, int32_t* out_labels, void* stream) {
+  if (!h) return fail(PLLB_ERR_INVALID, "null handle");
+  if (n_hyp <= 0) return PLLB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  PLLB_CUDA(cudaSetDevice(h->device));
+  int64_t copies = 0, rows = 0;
+  for (int32_t i = 0; i < n_hyp; ++i) {
+    const int64_t L = off[i + 1] - off[i];
+    copies += L;
+    rows += L * (L + 2);
+  }
+  if (copies > h->cap_copies || rows > INT32_MAX || n_hyp > h->cap_hyps)
+    return fail(PLLB_ERR_OOM, "pllb_expand: input exceeds one chunk");
+  RC(ensure_meta(h, 3 * (int64_t)(n_hyp + 1), s));
+  int32_t* tok_off = h->meta_host;
+  int32_t* copy_base = tok_off + (n_hyp + 1);
+  int32_t* row_base = copy_base + (n_hyp + 1);
+  int64_t t = 0, cb = 0, rb = 0;
+  for (int32_t i = 0; i <= n_hyp; ++i) {
+    tok_off[i] = (int32_t)t; copy_base[i] = (int32_t)cb; row_base[i] = (int32_t)rb;
+    if (i < n_hyp) { const int64_t L = off[i + 1] - off[i]; t += L; cb += L; rb += L * (L + 2); }
+  }
+  PLLB_CUDA(cudaMemcpyAsync(h->meta_dev, h->meta_host, sizeof(int32_t) * 3 * (n_hyp + 1), cudaMemcpyHostToDevice, s));
+  const int32_t* d_tok_off = h->meta_dev;
+  hyp_tokens += off[0];
+  RC(launch_expand_plan(hyp_tokens, d_tok_off, d_tok_off + (n_hyp + 1), d_tok_off + 2 * (n_hyp + 1), n_hyp, h->plan, s));
+  RC(launch_expand_ids(hyp_tokens, d_tok_off, h->plan, (int32_t)copies, h->d.cls_id, h->d.sep_id, h->d.mask_id, out_ids,
+                       out_mask_pos, out_labels, s));
+  return PLLB_OK;
+}
+
+int pllb_get_stats(pllb_handle h, pllb_stats* out) {
+  if (!h || !out) return fail(PLLB_ERR_INVALID, "pllb_get_stats: null argument");
+  if (h->timing && h->have_total) {
+    PLLB_CUDA(cudaEventSynchronize(h->ev_end));
+    float total = 0.f, gemm = 0.f;
+    PLLB_CUDA(cudaEventElapsedTime(&total, h->ev_begin, h->ev_end));
+    for (int k = 0; k < G_KINDS; ++k) h->gemm_ms_kind[k] = 0.f;
+    for (size_t i = 0; i < h->timed_used; ++i) {
+      float ms = 0.f;
+      PLLB_CUDA(cudaEventElapsedTime(&ms, h->timed[i].start, h->timed[i].stop));
+      gemm += ms;
+      h->gemm_ms_kind[h->timed[i].kind] += ms;
+    }
+    h->stats.last_total_ms = total;
+    h->stats.last_gemm_ms = gemm;
+  }
+  *out = h->stats;
+  return PLLB_OK;
+}
+
+/* Per-GEMM-kind device time (ms) of the last timed pllb_score call and the FLOPs issued
+ * per kind since the last reset: order QKV, attn-out, FFN1, FFN2, head transform, decoder. */
+int pllb_get_gemm_breakdown(pllb_handle h, float* ms6, double* flops6) {
+  if (!h) return fail(PLLB_ERR_INVALID, "null handle");
+  for (int k = 0; k < G_KINDS; ++k) {
+    if (ms6) ms6[k] = h->gemm_ms_kind[k];
+    if (flops6) flops6[k] = h->gemm_flops_kind[k];
+  }
+  return PLLB_OK;
+}
+
+int pllb_reset_stats(pllb_handle h) {
+  if (!h) return fail(PLLB_ERR_INVALID, "null handle");
+  h->stats = pllb_stats{};
+  for (int k = 0; k < G_KINDS; ++k) { h->gemm_ms_kind[k] = 0.f; h->gemm_flops_kind[k] = 0.0; }
+  h->have_total = false;
+  return PLLB_OK;
+}
+
+int pllb_set_timing(pllb_handle h, int enable) {
+  if (!h) return fail(PLLB_ERR_INVALID, "null handle");
+  h->timing = enable != 0;
+  return PLLB_OK;
+}
+
+int pllb_debug_gemm(const uint16_t* A, const uint16_t* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                    int32_t epilogue, void* stream) {
+  RC(check_device());
+  if (epilogue < 0 || epilogue > 3) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm: epilogue must be 0..3");
+  return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, (cudaStream_t)stream);
+}
+
+int pllb_debug_gemm_simt(const uint16_t* A, const uint16_t* W, const float* bias, void* C, int32_t M, int32_t N,
+                         int32_t K, int32_t epilogue, void* stream) {
+  RC(check_device());
+  return launch_gemm_simt(A, W, bias, C, M, N, K, epilogue, (cudaStream_t)stream);
+}
+
+int pllb_debug_hidden(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets, int32_t n_hyp,
+                      int32_t upto_layer, float* out_hidden, void* stream) {
+  if (upto_layer < 0) return fail(PLLB_ERR_INVALID, "pllb_debug_hidden: upto_layer must be >= 0");
+  if (n_hyp > 0 && !hyp_offsets) return fail(PLLB_ERR_INVALID, "pllb_debug_hidden: hyp_offsets is null");
+  const int64_t o0 = n_hyp > 0 ? hyp_offsets[0] : 0;
+  return score_impl(h, hyp_tokens ? hyp_tokens + o0 : nullptr, hyp_offsets, n_hyp, nullptr, nullptr, upto_layer,
+                    out_hidden, (cudaStream_t)stream);
+}
+
+int pllb_levenshtein(const int32_t* ref_cp, const int64_t* ref_off, const int32_t* hyp_cp, const int64_t* hyp_off,
+                     const int32_t* pair_ref, int32_t n_pairs, int32_t max_len, int32_t* out_dist, void* stream) {
+  RC(check_device());
+  const int64_t before = g_launch_counter;
+  (void)before;
+  return launch_levenshtein(ref_cp, ref_off, hyp_cp, hyp_off, pair_ref, n_pairs, max_len, out_dist, (cudaStream_t)stream);
+}
+
+int pllb_levenshtein_host(const int32_t* ref_cp, const int64_t* ref_off, int32_t n_ref, const int32_t* hyp_cp,
+                          const int64_t* hyp_off, const int32_t* pair_ref, int32_t n_pairs, int32_t* out_dist) {
+  RC(check_device());
+  if (n_pairs <= 0) return PLLB_OK;
+  if (!ref_off || !hyp_off || !pair_ref || !out_dist) return fail(PLLB_ERR_INVALID, "pllb_levenshtein_host: null argument");
+  int32_t max_len = 0;
+  for (int32_t i = 0; i < n_pairs; ++i) {
+    max_len = std::max<int32_t>(max_len, (int32_t)(hyp_off[i + 1] - hyp_off[i]));
+    if (pair_ref[i] < 0 || pair_ref[i] >= n_ref) return fail(PLLB_ERR_INVALID, "pllb_levenshtein_host: pair_ref out of range");
+  }
+  const int64_t n_rc = ref_off[n_ref], n_hc = hyp_off[n_pairs];
+  const int64_t b0 = align_up(4 * std::max<int64_t>(n_rc, 1), 256), b1 = align_up(8 * (int64_t)(n_ref + 1), 256),
+                b2 = align_up(4 * std::max<int64_t>(n_hc, 1), 256), b3 = align_up(8 * (int64_t)(n_pairs + 1), 256),
+                b4 = align_up(4 * (int64_t)n_pairs, 256), b5 = b4;
+  uint8_t* base = nullptr;
+  PLLB_CUDA(cudaMalloc(&base, (size_t)(b0 + b1 + b2 + b3 + b4 + b5)));
+  int32_t* d_rc = (int32_t*)base;
+  int64_t* d_ro = (int64_t*)(base + b0);
+  int32_t* d_hc = (int32_t*)(base + b0 + b1);
+  int64_t* d_ho = (int64_t*)(base + b0 + b1 + b2);
+  int32_t* d_pr = (int32_t*)(base + b0 + b1 + b2 + b3);
+  int32_t* d_out = (int32_t*)(base + b0 + b1 + b2 + b3 + b4);
+  cudaStream_t s = 0;
+  int rc = PLLB_OK;
+  cudaError_t e = cudaSuccess;
+  if (n_rc > 0) e = cudaMemcpyAsync(d_rc, ref_cp, 4 * n_rc, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ro, ref_off, 8 * (n_ref + 1), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && n_hc > 0) e = cudaMemcpyAsync(d_hc, hyp_cp, 4 * n_hc, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ho, hyp_off, 8 * (n_pairs + 1), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pr, pair_ref, 4 * (int64_t)n_pairs, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) rc = launch_levenshtein(d_rc, d_ro, d_hc, d_ho, d_pr, n_pairs, max_len, d_out, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaMemcpyAsync(out_dist, d_out, 4 * (int64_t)n_pairs, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaStreamSynchronize(s);
+  cudaFree(base);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("pllb_levenshtein_host: ") + cudaGetErrorString(e));
+  return PLLB_OK;
+}
+
+int pllb_rescore_sweep(const double* am, const double* lm, const int64_t* len, const int32_t* dist, int32_t N,
+                       int32_t n_best, const double* weights, int32_t W, int32_t variant, int32_t* out_argmax,
+                       int64_t* out_edit_sum, void* stream) {
+  RC(check_device());
+  return launch_rescore_sweep(am, lm, len, dist, N, n_best, weights, W, variant, out_argmax, out_edit_sum,
+                              (cudaStream_t)stream);
+}
+
+int pllb_rescore_sweep_host(const double* am, const double* lm, const int64_t* len, const int32_t* dist, int32_t N,
+                            int32_t n_best, const double* weights, int32_t W, int32_t variant, int32_t* out_argmax,
+                            int64_t* out_edit_sum) {
+  RC(check_device());
+  if (N <= 0 || W <= 0) return PLLB_OK;
+  if (!am || !lm || !len || !weights || !out_argmax) return fail(PLLB_ERR_INVALID, "pllb_rescore_sweep_host: null argument");
+  const int64_t n = (int64_t)N * n_best;
+  const int64_t b_d = align_up(8 * n, 256), b_i = align_up(4 * n, 256), b_w = align_up(8 * (int64_t)W, 256),
+                b_a = align_up(4 * (int64_t)W * N, 256);
+  uint8_t* base = nullptr;
+  PLLB_CUDA(cudaMalloc(&base, (size_t)(3 * b_d + b_i + 2 * b_w + b_a)));
+  double* d_am = (double*)base;
+  double* d_lm = (double*)(base + b_d);
+  int64_t* d_len = (int64_t*)(base + 2 * b_d);
+  int32_t* d_dist = (int32_t*)(base + 3 * b_d);
+  double* d_w = (double*)(base + 3 * b_d + b_i);
+  int64_t* d_es = (int64_t*)(base + 3 * b_d + b_i + b_w);
+  int32_t* d_arg = (int32_t*)(base + 3 * b_d + b_i + 2 * b_w);
+  cudaStream_t s = 0;
+  int rc = PLLB_OK;
+  cudaError_t e = cudaMemcpyAsync(d_am, am, 8 * n, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_lm, lm, 8 * n, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_len, len, 8 * n, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && dist) e = cudaMemcpyAsync(d_dist, dist, 4 * n, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_w, weights, 8 * (int64_t)W, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    rc = launch_rescore_sweep(d_am, d_lm, d_len, dist ? d_dist : nullptr, N, n_best, d_w, W, variant, d_arg,
+                              out_edit_sum ? d_es : nullptr, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaMemcpyAsync(out_argmax, d_arg, 4 * (int64_t)W * N, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && rc == PLLB_OK && out_edit_sum)
+    e = cudaMemcpyAsync(out_edit_sum, d_es, 8 * (int64_t)W, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaStreamSynchronize(s);
+  cudaFree(base);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("pllb_rescore_sweep_host: ") + cudaGetErrorString(e));
+  return PLLB_OK;
+}
+
+int pllb_rescore_scores(const double* am, const double* lm, const int64_t* len, int32_t N, int32_t n_best, double weight,
+                        int32_t variant, double* out_scores, void* stream) {
+  RC(check_device());
+  return launch_rescore_scores(am, lm, len, N, n_best, weight, variant, out_scores, (cudaStream_t)stream);
+}
+
+}  // extern "C"

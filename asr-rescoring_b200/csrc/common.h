@@ -1,0 +1,104 @@
+// common.h — host-side helpers shared by the translation units of libpllb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/pllb.h"
+
+namespace pllb {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+extern thread_local int64_t g_launch_counter;   // kernels launched by this library on this thread
+
+#define PLLB_CUDA(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::pllb::fail(PLLB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+  } while (0)
+
+#define PLLB_LAUNCH_CHECK(name)                                                                \
+  do {                                                                                         \
+    ++::pllb::g_launch_counter;                                                                \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return ::pllb::fail(PLLB_ERR_CUDA, std::string("launch ") + name + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+int sm_count();   // SMs of the current device (cached)
+
+// ---- GEMM (gemm_tcgen05.cu) -------------------------------------------------
+enum GemmEpilogue : int {
+  EPI_BIAS_BF16 = 0,       // out bf16 = acc + bias
+  EPI_BIAS_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
+  EPI_BIAS_F32 = 2,        // out fp32 = acc + bias
+  EPI_BIAS_GELU_F32 = 3,   // out fp32 = gelu_erf(acc + bias)
+  EPI_LSE = 4              // vocab-tiled online logsumexp + label-column pick (no C output)
+};
+
+struct LseArgs {
+  const int32_t* labels;   // [M] label column of each row
+  float2* partials;        // [M, n_tiles_n] (running max, sum of exp) per vocab tile
+  float* label_logit;      // [M] written by the tile that owns the label column
+  int32_t vocab;           // real vocab size (columns >= vocab are masked)
+};
+
+// C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A, W bf16 row-major (K contiguous).
+// N % 256 == 0 (pad W rows with zeros), K % 64 == 0.  ldc = N.
+int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
+                        int epilogue, const LseArgs* lse, cudaStream_t stream);
+int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
+                     int epilogue, cudaStream_t stream);
+
+// ---- encoder pieces (encoder_kernels.cu) -------------------------------------
+struct CopyPlan {          // device arrays, one entry per masked copy of the chunk
+  int32_t* seq_start;      // first packed row of the copy
+  int32_t* seq_len;        // T = L + 2
+  int32_t* mask_row;       // packed row index of the [MASK] token
+  int32_t* label;          // original token at the masked position
+  int32_t* hyp;            // chunk-local hypothesis index
+};
+
+int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
+                       const int32_t* hyp_row_base, int32_t n_hyp, CopyPlan plan, cudaStream_t s);
+int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
+                      int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t* out_ids, int32_t* out_mask_pos,
+                      int32_t* out_labels, cudaStream_t s);
+int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
+                    const float* word_emb, const float* pos_emb, const float* type_emb, const float* g,
+                    const float* b, float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id,
+                    float* hidden_f32, void* hidden_bf16, cudaStream_t s);
+// hidden = LN(y + hidden) (in place), hidden_bf16 = bf16(hidden)
+int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b,
+                       float eps, int64_t rows, int H, cudaStream_t s);
+// out_bf16 = bf16(LN(x)); no residual (MLM head transform)
+int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const float* b, float eps, int64_t rows,
+                         int H, cudaStream_t s);
+int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
+                     int max_T, cudaStream_t s);
+int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out,
+                            cudaStream_t s);
+int launch_lse_finish(const float2* partials, const float* label_logit, int32_t n_copies, int n_tiles,
+                      float* tok_logp, cudaStream_t s);
+int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,
+                   float* out_tok_logp, cudaStream_t s);
+int launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
+
+// ---- combiner (rescore_kernels.cu, compiled with -fmad=false) ------------------
+int launch_rescore_sweep(const double* am, const double* lm, const int64_t* len, const int32_t* dist, int32_t N,
+                         int32_t n_best, const double* weights, int32_t W, int32_t variant, int32_t* out_argmax,
+                         int64_t* out_edit_sum, cudaStream_t s);
+int launch_rescore_scores(const double* am, const double* lm, const int64_t* len, int32_t N, int32_t n_best,
+                          double weight, int32_t variant, double* out, cudaStream_t s);
+int launch_levenshtein(const int32_t* ref_cp, const int64_t* ref_off, const int32_t* hyp_cp, const int64_t* hyp_off,
+                       const int32_t* pair_ref, int32_t n_pairs, int32_t max_len, int32_t* out, cudaStream_t s);
+
+}  // namespace pllb

@@ -1,0 +1,463 @@
+// encoder_kernels.cu — the HBM-bound pieces of the MLM-PLL path for sm_100a:
+//   stage 1  masked-copy expansion with varlen packing (replaces MLM_PLL/preprocess.py:9-30
+//            and the padded collate of MLM_PLL/main.py:28-54), fused with BertEmbeddings
+//            (transformers modeling_bert.py:72-112);
+//   LayerNorm with residual (modeling_bert.py:294-298, 352-356), per-sequence varlen
+//            self-attention (:168-207), masked-row gather, logsumexp finish and the
+//            per-hypothesis sum of MLM_PLL/main.py:101-107.
+// All kernels are one-warp-per-row (or per sequence/head) with 128-bit accesses; rows of
+// H fp32 are contiguous so every warp access is a fully coalesced 512-byte segment.
+#include <cuda_bf16.h>
+
+#include "common.h"
+
+namespace pllb {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------- plan
+// One thread per hypothesis: writes the descriptors of its L masked copies.
+__global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off,
+                                   const int32_t* __restrict__ hyp_copy_base, const int32_t* __restrict__ hyp_row_base,
+                                   int32_t n_hyp, CopyPlan plan) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hyp) return;
+  const int t0 = hyp_tok_off[h];
+  const int L = hyp_tok_off[h + 1] - t0;
+  const int T = L + 2;
+  const int c0 = hyp_copy_base[h];
+  const int r0 = hyp_row_base[h];
+  for (int m = 0; m < L; ++m) {
+    const int c = c0 + m;
+    plan.seq_start[c] = r0 + m * T;
+    plan.seq_len[c] = T;
+    plan.mask_row[c] = r0 + m * T + m + 1;
+    plan.label[c] = tokens[t0 + m];
+    plan.hyp[c] = h;
+  }
+}
+
+__device__ __forceinline__ int copy_token_id(const int32_t* __restrict__ tokens, int t0, int T, int m, int p,
+                                             int cls_id, int sep_id, int mask_id) {
+  // [CLS] t[:m] [MASK] t[m+1:] [SEP] — MLM_PLL/preprocess.py:16-22
+  if (p == 0) return cls_id;
+  if (p == T - 1) return sep_id;
+  if (p == m + 1) return mask_id;
+  return tokens[t0 + p - 1];
+}
+
+// Materialises input_ids / mask_pos / labels (parity hook for stage 1; the scoring path
+// never writes ids to HBM, see embed_ln_kernel).
+__global__ void expand_ids_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off,
+                                  CopyPlan plan, int32_t n_copies, int cls_id, int sep_id, int mask_id,
+                                  int32_t* __restrict__ out_ids, int32_t* __restrict__ out_mask_pos,
+                                  int32_t* __restrict__ out_labels) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n_copies) return;
+  const int start = plan.seq_start[c], T = plan.seq_len[c];
+  const int m = plan.mask_row[c] - start - 1;
+  const int t0 = hyp_tok_off[plan.hyp[c]];
+  for (int p = lane; p < T; p += 32) out_ids[start + p] = copy_token_id(tokens, t0, T, m, p, cls_id, sep_id, mask_id);
+  if (lane == 0) {
+    out_mask_pos[c] = m + 1;
+    out_labels[c] = plan.label[c];
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm helpers
+// A warp owns one row of H = 128 * VEC floats; lane holds VEC float4 (columns 4*(lane+32*i)..).
+template <int VEC>
+__device__ __forceinline__ void ln_normalize(float4 (&x)[VEC], const float* __restrict__ g, const float* __restrict__ b,
+                                             float eps, int lane) {
+  constexpr float inv_h = 1.0f / (128.0f * VEC);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+  const float mean = warp_sum(s) * inv_h;
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = x[i].x - mean, bb = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+    v += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(v) * inv_h + eps);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    x[i].x = (x[i].x - mean) * rstd * gg.x + be.x;
+    x[i].y = (x[i].y - mean) * rstd * gg.y + be.y;
+    x[i].z = (x[i].z - mean) * rstd * gg.z + be.z;
+    x[i].w = (x[i].w - mean) * rstd * gg.w + be.w;
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_row(const float4 (&x)[VEC], float* __restrict__ f32_row,
+                                          __nv_bfloat16* __restrict__ bf_row, int lane) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (f32_row) reinterpret_cast<float4*>(f32_row)[lane + 32 * i] = x[i];
+    if (bf_row) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(x[i].x, x[i].y), hi = __floats2bfloat162_rn(x[i].z, x[i].w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(bf_row)[lane + 32 * i] = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- stage 1 + BertEmbeddings
+// One warp per masked copy: derives every token id of the copy on the fly (ids never touch
+// HBM), gathers word + position + token_type(0) rows, LayerNorm, writes the fp32 residual
+// stream and the bf16 GEMM operand.
+template <int VEC>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off, CopyPlan plan,
+                int32_t n_copies, const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
+                const float* __restrict__ type_emb, const float* __restrict__ g, const float* __restrict__ b, float eps,
+                int cls_id, int sep_id, int mask_id, float* __restrict__ hidden_f32,
+                __nv_bfloat16* __restrict__ hidden_bf16) {
+  constexpr int H = 128 * VEC;
+  const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n_copies) return;
+  const int start = plan.seq_start[c], T = plan.seq_len[c];
+  const int m = plan.mask_row[c] - start - 1;
+  const int t0 = hyp_tok_off[plan.hyp[c]];
+  for (int p = 0; p < T; ++p) {
+    const int id = copy_token_id(tokens, t0, T, m, p, cls_id, sep_id, mask_id);
+    const float4* w = reinterpret_cast<const float4*>(word_emb + (size_t)id * H);
+    const float4* pe = reinterpret_cast<const float4*>(pos_emb + (size_t)p * H);
+    const float4* te = reinterpret_cast<const float4*>(type_emb);
+    float4 x[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 a = __ldg(w + lane + 32 * i), bb = __ldg(te + lane + 32 * i), cc = __ldg(pe + lane + 32 * i);
+      // (word + token_type) + position — modeling_bert.py:104-108
+      x[i].x = (a.x + bb.x) + cc.x; x[i].y = (a.y + bb.y) + cc.y;
+      x[i].z = (a.z + bb.z) + cc.z; x[i].w = (a.w + bb.w) + cc.w;
+    }
+    ln_normalize<VEC>(x, g, b, eps, lane);
+    const size_t row = (size_t)(start + p);
+    store_row<VEC>(x, hidden_f32 + row * H, hidden_bf16 + row * H, lane);
+  }
+}
+
+// hidden = LayerNorm(y + hidden) in place (+ bf16 copy).  One warp per row.
+template <int VEC, bool RESID>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+ln_kernel(const float* __restrict__ y, float* __restrict__ hidden_f32, __nv_bfloat16* __restrict__ out_bf16,
+          const float* __restrict__ g, const float* __restrict__ b, float eps, int64_t rows) {
+  constexpr int H = 128 * VEC;
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* yr = reinterpret_cast<const float4*>(y + row * H);
+  float4 x[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) x[i] = yr[lane + 32 * i];
+  if (RESID) {
+    const float4* hr = reinterpret_cast<const float4*>(hidden_f32 + row * H);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float4 r = hr[lane + 32 * i];
+      x[i].x += r.x; x[i].y += r.y; x[i].z += r.z; x[i].w += r.w;
+    }
+  }
+  ln_normalize<VEC>(x, g, b, eps, lane);
+  store_row<VEC>(x, RESID ? hidden_f32 + row * H : nullptr, out_bf16 + row * H, lane);
+}
+
+// ---------------------------------------------------------------- varlen self-attention
+// One warp per (masked copy, head).  K^T and V of the head are staged in shared memory as
+// bf16; 4 query rows are processed together; softmax in fp32 with an online update over
+// 32-key tiles, so any T up to max_position works.  qkv row layout: [Q(H) | K(H) | V(H)].
+constexpr int ATT_QB = 4;
+
+__global__ void attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
+                                 int32_t n_copies, int H, int NH, int Tp /* padded T, odd */, int warps_per_block) {
+  extern __shared__ uint8_t att_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * warps_per_block + wib;
+  if (pair >= (int64_t)n_copies * NH) return;
+  const int c = (int)(pair / NH), head = (int)(pair % NH);
+  const int start = plan.seq_start[c], T = plan.seq_len[c];
+  // per-warp shared memory: Kt[64][Tp] bf16 | V[Tp][64] bf16 | qs[64][4] f32 | ps[32][4] f32
+  const size_t per_warp = (size_t)64 * Tp * 2 + (size_t)Tp * 64 * 2 + 64 * ATT_QB * 4 + 32 * ATT_QB * 4;
+  uint8_t* base = att_smem + (size_t)wib * ((per_warp + 15) & ~(size_t)15);
+  __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* Vs = Kt + 64 * Tp;
+  float* qs = reinterpret_cast<float*>(Vs + (size_t)Tp * 64);
+  float* ps = qs + 64 * ATT_QB;
+  const size_t ld = (size_t)3 * H;
+  const __nv_bfloat16* qbase = qkv + (size_t)start * ld + head * 64;
+  const __nv_bfloat16* kbase = qbase + H;
+  const __nv_bfloat16* vbase = qbase + 2 * H;
+
+  for (int j = 0; j < T; ++j) {
+    const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(kbase + (size_t)j * ld + 2 * lane);
+    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)j * ld + 2 * lane);
+    Kt[(2 * lane) * Tp + j] = k2.x;
+    Kt[(2 * lane + 1) * Tp + j] = k2.y;
+    *reinterpret_cast<__nv_bfloat162*>(Vs + (size_t)j * 64 + 2 * lane) = v2;
+  }
+  __syncwarp();
+
+  for (int i0 = 0; i0 < T; i0 += ATT_QB) {
+    // stage the query block: qs[d][a] = Q[i0+a][d]
+#pragma unroll
+    for (int a = 0; a < ATT_QB; ++a) {
+      const int i = min(i0 + a, T - 1);
+      const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(qbase + (size_t)i * ld + 2 * lane);
+      qs[(2 * lane) * ATT_QB + a] = __bfloat162float(q2.x);
+      qs[(2 * lane + 1) * ATT_QB + a] = __bfloat162float(q2.y);
+    }
+    __syncwarp();
+    float mx[ATT_QB], l[ATT_QB], o0[ATT_QB], o1[ATT_QB];
+#pragma unroll
+    for (int a = 0; a < ATT_QB; ++a) { mx[a] = -INFINITY; l[a] = 0.f; o0[a] = 0.f; o1[a] = 0.f; }
+    for (int kt = 0; kt < T; kt += 32) {
+      const int key = kt + lane;
+      const bool valid = key < T;
+      const int keyc = valid ? key : T - 1;
+      float s[ATT_QB];
+#pragma unroll
+      for (int a = 0; a < ATT_QB; ++a) s[a] = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < 64; ++d) {
+        const float kv = __bfloat162float(Kt[d * Tp + keyc]);
+        const float4 q4 = *reinterpret_cast<const float4*>(qs + d * ATT_QB);
+        s[0] += q4.x * kv; s[1] += q4.y * kv; s[2] += q4.z * kv; s[3] += q4.w * kv;
+      }
+      float p[ATT_QB];
+#pragma unroll
+      for (int a = 0; a < ATT_QB; ++a) {
+        const float sc = valid ? s[a] * 0.125f : -INFINITY;    // scaling = head_dim ** -0.5
+        const float tmax = warp_max(sc);
+        const float nm = fmaxf(mx[a], tmax);
+        p[a] = valid ? __expf(sc - nm) : 0.f;
+        const float tsum = warp_sum(p[a]);
+        const float corr = __expf(mx[a] - nm);                 // exp(-inf) = 0 on the first tile
+        l[a] = l[a] * corr + tsum;
+        o0[a] *= corr; o1[a] *= corr;
+        mx[a] = nm;
+      }
+      __syncwarp();
+      *reinterpret_cast<float4*>(ps + lane * ATT_QB) = make_float4(p[0], p[1], p[2], p[3]);
+      __syncwarp();
+      const int nk = min(32, T - kt);
+      for (int j = 0; j < nk; ++j) {
+        const float4 p4 = *reinterpret_cast<const float4*>(ps + j * ATT_QB);
+        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(Vs + (size_t)(kt + j) * 64 + 2 * lane);
+        const float vx = __bfloat162float(v2.x), vy = __bfloat162float(v2.y);
+        o0[0] += p4.x * vx; o1[0] += p4.x * vy;
+        o0[1] += p4.y * vx; o1[1] += p4.y * vy;
+        o0[2] += p4.z * vx; o1[2] += p4.z * vy;
+        o0[3] += p4.w * vx; o1[3] += p4.w * vy;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < ATT_QB; ++a) {
+      const int i = i0 + a;
+      if (i < T) {
+        const float inv = 1.0f / l[a];
+        *reinterpret_cast<__nv_bfloat162*>(ctx + (size_t)(start + i) * H + head * 64 + 2 * lane) =
+            __floats2bfloat162_rn(o0[a] * inv, o1[a] * inv);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- head helpers
+__global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows,
+                                        int32_t n, int H, __nv_bfloat16* __restrict__ dst) {
+  const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n) return;
+  const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)rows[c] * H);
+  uint4* d = reinterpret_cast<uint4*>(dst + (size_t)c * H);
+  for (int i = lane; i < H / 8; i += 32) d[i] = s[i];
+}
+
+// log_softmax(logits)[label] = label_logit - (max + log(sum exp)) — MLM_PLL/main.py:101-105
+__global__ void lse_finish_kernel(const float2* __restrict__ partials, const float* __restrict__ label_logit,
+                                  int32_t n_copies, int n_tiles, float* __restrict__ tok_logp) {
+  const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n_copies) return;
+  const float2* pr = partials + (size_t)c * n_tiles;
+  float m = -INFINITY;
+  for (int t = lane; t < n_tiles; t += 32) m = fmaxf(m, pr[t].x);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int t = lane; t < n_tiles; t += 32) {
+    const float2 v = pr[t];
+    if (v.y > 0.f) s += v.y * expf(v.x - m);
+  }
+  s = warp_sum(s);
+  if (lane == 0) tok_logp[c] = (label_logit[c] - m) - logf(s);
+}
+
+// output_score[u][h] += s over the L copies, in order, in double — MLM_PLL/main.py:106-107
+__global__ void hyp_sum_kernel(const float* __restrict__ tok_logp, const int32_t* __restrict__ hyp_copy_base,
+                               int32_t n_hyp, double* __restrict__ out_pll, float* __restrict__ out_tok_logp) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hyp) return;
+  const int c0 = hyp_copy_base[h], c1 = hyp_copy_base[h + 1];
+  double acc = 0.0;
+  for (int c = c0; c < c1; ++c) {
+    const float v = tok_logp[c];
+    acc += (double)v;
+    if (out_tok_logp) out_tok_logp[c] = v;
+  }
+  out_pll[h] = acc;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + i) = u;
+  } else {
+    for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
+                       const int32_t* hyp_row_base, int32_t n_hyp, CopyPlan plan, cudaStream_t s) {
+  if (n_hyp <= 0) return PLLB_OK;
+  expand_plan_kernel<<<(unsigned)ceil_div(n_hyp, 128), 128, 0, s>>>(tokens, hyp_tok_off, hyp_copy_base, hyp_row_base,
+                                                                   n_hyp, plan);
+  PLLB_LAUNCH_CHECK("expand_plan_kernel");
+  return PLLB_OK;
+}
+
+int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
+                      int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t* out_ids, int32_t* out_mask_pos,
+                      int32_t* out_labels, cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  expand_ids_kernel<<<(unsigned)ceil_div(n_copies, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(
+      tokens, hyp_tok_off, plan, n_copies, cls_id, sep_id, mask_id, out_ids, out_mask_pos, out_labels);
+  PLLB_LAUNCH_CHECK("expand_ids_kernel");
+  return PLLB_OK;
+}
+
+#define PLLB_DISPATCH_VEC(H, CALL)                                                   \
+  switch ((H) / 128) {                                                               \
+    case 2: { constexpr int VEC = 2; CALL; } break;                                  \
+    case 4: { constexpr int VEC = 4; CALL; } break;                                  \
+    case 6: { constexpr int VEC = 6; CALL; } break;                                  \
+    case 8: { constexpr int VEC = 8; CALL; } break;                                  \
+    default: return fail(PLLB_ERR_INVALID, "hidden size must be 256, 512, 768 or 1024"); \
+  }
+
+int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
+                    const float* word_emb, const float* pos_emb, const float* type_emb, const float* g, const float* b,
+                    float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id, float* hidden_f32,
+                    void* hidden_bf16, cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  const unsigned grid = (unsigned)ceil_div(n_copies, WARPS_PER_BLOCK);
+  PLLB_DISPATCH_VEC(H, (embed_ln_kernel<VEC><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
+                           tokens, hyp_tok_off, plan, n_copies, word_emb, pos_emb, type_emb, g, b, eps, cls_id, sep_id,
+                           mask_id, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_bf16))));
+  PLLB_LAUNCH_CHECK("embed_ln_kernel");
+  return PLLB_OK;
+}
+
+int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b, float eps,
+                       int64_t rows, int H, cudaStream_t s) {
+  if (rows <= 0) return PLLB_OK;
+  const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
+  PLLB_DISPATCH_VEC(H, (ln_kernel<VEC, true><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
+                           y, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_bf16), g, b, eps, rows)));
+  PLLB_LAUNCH_CHECK("ln_kernel<resid>");
+  return PLLB_OK;
+}
+
+int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const float* b, float eps, int64_t rows, int H,
+                         cudaStream_t s) {
+  if (rows <= 0) return PLLB_OK;
+  const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
+  PLLB_DISPATCH_VEC(H, (ln_kernel<VEC, false><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
+                           x, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), g, b, eps, rows)));
+  PLLB_LAUNCH_CHECK("ln_kernel<plain>");
+  return PLLB_OK;
+}
+
+int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH, int max_T,
+                     cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
+  const int Tp = max_T | 1;
+  size_t per_warp = (size_t)64 * Tp * 2 + (size_t)Tp * 64 * 2 + 64 * ATT_QB * 4 + 32 * ATT_QB * 4;
+  per_warp = (per_warp + 15) & ~(size_t)15;
+  int wpb = 8;
+  while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
+  const size_t smem = per_warp * wpb;
+  if (smem > 200 * 1024) return fail(PLLB_ERR_TOO_LONG, "attention: sequence too long for shared memory");
+  PLLB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t pairs = (int64_t)n_copies * NH;
+  attention_kernel<<<(unsigned)ceil_div(pairs, wpb), wpb * 32, smem, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
+      NH, Tp, wpb);
+  PLLB_LAUNCH_CHECK("attention_kernel");
+  return PLLB_OK;
+}
+
+int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out, cudaStream_t s) {
+  if (n <= 0) return PLLB_OK;
+  gather_rows_bf16_kernel<<<(unsigned)ceil_div(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(hidden_bf16), rows, n, H, reinterpret_cast<__nv_bfloat16*>(out));
+  PLLB_LAUNCH_CHECK("gather_rows_bf16_kernel");
+  return PLLB_OK;
+}
+
+int launch_lse_finish(const float2* partials, const float* label_logit, int32_t n_copies, int n_tiles, float* tok_logp,
+                      cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  lse_finish_kernel<<<(unsigned)ceil_div(n_copies, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(
+      partials, label_logit, n_copies, n_tiles, tok_logp);
+  PLLB_LAUNCH_CHECK("lse_finish_kernel");
+  return PLLB_OK;
+}
+
+int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,
+                   float* out_tok_logp, cudaStream_t s) {
+  if (n_hyp <= 0) return PLLB_OK;
+  hyp_sum_kernel<<<(unsigned)ceil_div(n_hyp, 128), 128, 0, s>>>(tok_logp, hyp_copy_base, n_hyp, out_pll, out_tok_logp);
+  PLLB_LAUNCH_CHECK("hyp_sum_kernel");
+  return PLLB_OK;
+}
+
+int launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
+  if (n <= 0) return PLLB_OK;
+  f32_to_bf16_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  PLLB_LAUNCH_CHECK("f32_to_bf16_kernel");
+  return PLLB_OK;
+}
+
+}  // namespace pllb

@@ -1,0 +1,427 @@
+// gemm_tcgen05.cu — the encoder / MLM-head GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
+//
+// A (activations) and W (nn.Linear weight, [out,in]) are both K-contiguous bf16, so the
+// "TN" form maps straight onto K-major UMMA operands with no transposes.  This replaces
+// the six F.linear calls per BertLayer of transformers' modeling_bert.py:179-181,295,340,353
+// and the MLM head's transform / decoder (:481-501) that MLM_PLL/main.py:89-94 invokes.
+//
+// Design (one CTA per SM, persistent over output tiles):
+//   warp 0   : TMA producer — cp.async.bulk.tensor loads of a 128x64 A box and a 256x64 W
+//              box (128-byte swizzle) into a 4-stage shared-memory ring, mbarrier-tracked.
+//   warp 1   : MMA issuer — one thread issues tcgen05.mma (M=128, N=256, K=16) x4 per
+//              stage; accumulators live in TMEM (2 x 256 fp32 columns, double buffered so
+//              the epilogue of tile i overlaps the MMAs of tile i+1); tcgen05.commit frees
+//              smem stages and publishes finished accumulators.
+//   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp), bias / erf-GELU /
+//              dtype conversion in registers, 128-byte-swizzled staging in shared memory
+//              and TMA stores; or, for the decoder, an online logsumexp over the vocab
+//              tile plus the label-column pick, so the [copies x V] logits never exist.
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pllb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;      // one 32-row x 128-byte swizzled box
+constexpr int EPI_BUFS = 2;                  // per epilogue warp
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int TMEM_COLS = 512;               // 2 accumulator stages x BN columns
+constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+constexpr int SMEM_EPI = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
+constexpr int SMEM_BARS = 256;
+constexpr int SMEM_TOTAL = SMEM_PIPE + SMEM_EPI + SMEM_BARS + 1024;  // + alignment slack
+
+struct KParams {
+  int M, N, K;
+  const float* bias;
+  LseArgs lse;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // HF activations "gelu" = nn.functional.gelu (erf form)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t sEpi = smem_base + SMEM_PIPE;
+  const uint32_t sBar = sEpi + SMEM_EPI;
+  const uint32_t bar_full = sBar;                 // STAGES x 8 B
+  const uint32_t bar_empty = sBar + 8 * STAGES;   // STAGES x 8 B
+  const uint32_t bar_tfull = sBar + 16 * STAGES;  // 2 x 8 B
+  const uint32_t bar_tempty = bar_tfull + 16;     // 2 x 8 B
+  const uint32_t tmem_slot = bar_tempty + 16;     // 4 B
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_n = p.N / BN;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    if (EPI != EPI_LSE) prefetch_tensormap(&tmC);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_tfull + 8 * s, 1);
+        mbar_init(bar_tempty + 8 * s, EPI_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM;
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m0);
+          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);         // TMA bytes landed
+          tcgen05_fence_after();
+          const uint32_t a_addr = sA + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = sB + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2);
+            const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2);
+            tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(bar_empty + 8 * stage);          // smem stage reusable once MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(bar_tfull + 8 * acc);              // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                               // TMEM lane quarter this warp may read
+    const int ew = warp - 2;
+    const uint32_t my_buf = sEpi + ew * EPI_BUFS * EPI_BUF_BYTES;
+    uint32_t acc = 0, acc_phase = 0;
+    uint32_t buf_i = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM;
+      const int tn = tile % tiles_n;
+      const int n0 = tn * BN;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+
+      if constexpr (EPI == EPI_LSE) {
+        const int label = (row < p.M) ? p.lse.labels[row] : -1;
+        float run_max = -INFINITY, run_sum = 0.f, lab_val = 0.f;
+        bool has_label = false;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c0, r);
+          tcgen05_wait_ld();
+          float x[32];
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            float v = __uint_as_float(r[j]) + __ldg(p.bias + col);
+            if (col >= p.lse.vocab) v = -INFINITY;
+            if (col == label) { lab_val = v; has_label = true; }
+            x[j] = v;
+            cmax = fmaxf(cmax, v);
+          }
+          if (cmax > -INFINITY) {
+            const float new_max = fmaxf(run_max, cmax);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += __expf(x[j] - new_max);
+            run_sum = run_sum * __expf(run_max - new_max) + s;
+            run_max = new_max;
+          }
+        }
+        if (row < p.M) {
+          p.lse.partials[(size_t)row * tiles_n + tn] = make_float2(run_max, run_sum);
+          if (has_label) p.lse.label_logit[row] = lab_val;
+        }
+      } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_addr + c0, r0);
+          tmem_ld_32x32b_x32(t_addr + c0 + 32, r1);
+          tcgen05_wait_ld();
+          const uint32_t buf = my_buf + (buf_i & 1) * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();         // the store that last read this buffer is done
+          __syncwarp();
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                    // 8 chunks of 8 bf16 (16 B)
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int cc = c * 8 + j;
+              v[j] = __uint_as_float(cc < 32 ? r0[cc] : r1[cc - 32]);
+            }
+            const float4 b0 = __ldg(bias4 + 2 * c), b1 = __ldg(bias4 + 2 * c + 1);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            if constexpr (EPI == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+            }
+            const uint32_t dst = buf + lane * 128 + ((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(v[0], v[1])),
+                         "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n0 + c0, m0 + q * 32);
+            tma_store_commit();
+          }
+          ++buf_i;
+        }
+      } else {  // fp32 output
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_addr + c0, r);
+          tcgen05_wait_ld();
+          const uint32_t buf = my_buf + (buf_i & 1) * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                    // 8 chunks of 4 fp32 (16 B)
+            const float4 b = __ldg(bias4 + c);
+            float v0 = __uint_as_float(r[4 * c + 0]) + b.x;
+            float v1 = __uint_as_float(r[4 * c + 1]) + b.y;
+            float v2 = __uint_as_float(r[4 * c + 2]) + b.z;
+            float v3 = __uint_as_float(r[4 * c + 3]) + b.w;
+            if constexpr (EPI == EPI_BIAS_GELU_F32) {
+              v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
+            }
+            const uint32_t dst = buf + lane * 128 + ((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(__float_as_uint(v0)),
+                         "r"(__float_as_uint(v1)), "r"(__float_as_uint(v2)), "r"(__float_as_uint(v3))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n0 + c0, m0 + q * 32);
+            tma_store_commit();
+          }
+          ++buf_i;
+        }
+      }
+      // all tcgen05.ld of this accumulator have completed (wait::ld above): release it
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D row-major tensor [rows, cols] of `elt_bytes`-byte elements; box = [box_rows, box_cols],
+// 128-byte swizzle (box_cols * elt_bytes must be 128).
+int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows, uint64_t cols,
+              uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * (uint64_t)elt_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+  return PLLB_OK;
+}
+
+template <int EPI>
+int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
+               cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    PLLB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured = true;
+  }
+  gemm_tcgen05_kernel<EPI><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(a, b, c, kp);
+  PLLB_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  return PLLB_OK;
+}
+
+}  // namespace
+
+int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
+                        int epilogue, const LseArgs* lse, cudaStream_t stream) {
+  if (M <= 0) return PLLB_OK;
+  if (N % BN != 0 || K % BK != 0 || M > INT32_MAX)
+    return fail(PLLB_ERR_INVALID, "gemm: need N % 256 == 0 and K % 64 == 0");
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
+  if ((rc = make_tmap(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, BN, BK))) return rc;
+  tc = ta;
+  if (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16) {
+    if ((rc = make_tmap(&tc, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)N, 32, 64))) return rc;
+  } else if (epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_GELU_F32) {
+    if ((rc = make_tmap(&tc, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)N, 32, 32))) return rc;
+  }
+  KParams kp{};
+  kp.M = (int)M; kp.N = N; kp.K = K; kp.bias = bias;
+  if (epilogue == EPI_LSE) {
+    if (!lse) return fail(PLLB_ERR_INVALID, "gemm: LSE epilogue needs LseArgs");
+    kp.lse = *lse;
+  }
+  const int64_t tiles = ceil_div(M, BM) * (N / BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  switch (epilogue) {
+    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, stream);
+    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, stream);
+    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, stream);
+    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, stream);
+  }
+  return fail(PLLB_ERR_INVALID, "gemm: unknown epilogue");
+}
+
+// ------------------------------------------------------------------ SIMT validation kernel
+// Plain shared-memory-tiled GEMM with the same operand rounding and epilogues; used by
+// tests to localise errors of the tcgen05 path (never on the timed path).
+namespace {
+template <int EPI>
+__global__ void gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
+                                 const float* __restrict__ bias, void* __restrict__ C, int M, int N, int K) {
+  __shared__ float As[16][17], Ws[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    As[ty][tx] = (row < M) ? __bfloat162float(A[(size_t)row * K + k0 + tx]) : 0.f;
+    const int wrow = blockIdx.x * 16 + ty;
+    Ws[ty][tx] = (wrow < N) ? __bfloat162float(W[(size_t)wrow * K + k0 + tx]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += As[ty][k] * Ws[tx][k];
+    __syncthreads();
+  }
+  if (row < M && col < N) {
+    float v = acc + bias[col];
+    if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_F32) v = gelu_erf(v);
+    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16)
+      reinterpret_cast<__nv_bfloat16*>(C)[(size_t)row * N + col] = __float2bfloat16_rn(v);
+    else
+      reinterpret_cast<float*>(C)[(size_t)row * N + col] = v;
+  }
+}
+}  // namespace
+
+int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K, int epilogue,
+                     cudaStream_t stream) {
+  if (M <= 0) return PLLB_OK;
+  if (K % 16 != 0) return fail(PLLB_ERR_INVALID, "gemm_simt: K % 16 != 0");
+  dim3 block(16, 16), grid((unsigned)ceil_div(N, 16), (unsigned)ceil_div(M, 16));
+  const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(A);
+  const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(W);
+  switch (epilogue) {
+    case EPI_BIAS_BF16: gemm_simt_kernel<EPI_BIAS_BF16><<<grid, block, 0, stream>>>(a, w, bias, C, (int)M, N, K); break;
+    case EPI_BIAS_GELU_BF16: gemm_simt_kernel<EPI_BIAS_GELU_BF16><<<grid, block, 0, stream>>>(a, w, bias, C, (int)M, N, K); break;
+    case EPI_BIAS_F32: gemm_simt_kernel<EPI_BIAS_F32><<<grid, block, 0, stream>>>(a, w, bias, C, (int)M, N, K); break;
+    case EPI_BIAS_GELU_F32: gemm_simt_kernel<EPI_BIAS_GELU_F32><<<grid, block, 0, stream>>>(a, w, bias, C, (int)M, N, K); break;
+    default: return fail(PLLB_ERR_INVALID, "gemm_simt: unsupported epilogue");
+  }
+  PLLB_LAUNCH_CHECK("gemm_simt_kernel");
+  return PLLB_OK;
+}
+
+}  // namespace pllb

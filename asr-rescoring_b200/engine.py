@@ -1,0 +1,301 @@
+"""Host-side driver of libpllb200.so: weight handoff, PLL scoring, Levenshtein, λ-sweep.
+
+PyTorch is used only to own device memory (weights on their way in, caller-visible
+outputs) and for the current CUDA stream; all arithmetic happens in the library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import LayerWeights, ModelDesc, Stats, Weights, check
+
+VARIANTS = {"B": 0, "A": 1, "C": 2, 0: 0, 1: 1, 2: 2}
+GEMM_KINDS = ("qkv", "attn_out", "ffn1", "ffn2", "head_transform", "decoder_lse")
+
+
+def _np_ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class PllScorer:
+    """BERT masked-LM pseudo-log-likelihood scorer; stands in for the
+    ``BertForMaskedLM`` + ``run_one_epoch(do_scoring=True)`` pair of
+    MLM_PLL/main.py:73-114,184-187."""
+
+    def __init__(self, state_dict: Dict[str, "torch.Tensor"], cfg: Optional[dict] = None, device: int = 0,
+                 max_chunk_tokens: int = 0, cls_id: int = 101, sep_id: int = 102, mask_id: int = 103):
+        import torch
+        from .synth import config_from_state_dict
+
+        self._lib = _lib.load()
+        _lib.require_device()
+        self._h = ctypes.c_void_p()
+        self.cfg = dict(cfg) if cfg is not None else config_from_state_dict(state_dict)
+        self.device = device
+        dev = torch.device("cuda", device)
+        keep = []
+
+        def dp(key):
+            t = state_dict[key].detach().to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return ctypes.c_void_p(t.data_ptr())
+
+        nl = self.cfg["num_layers"]
+        layers = (LayerWeights * max(nl, 1))()
+        for i in range(nl):
+            p = f"bert.encoder.layer.{i}."
+            lw = layers[i]
+            lw.q_w, lw.q_b = dp(p + "attention.self.query.weight"), dp(p + "attention.self.query.bias")
+            lw.k_w, lw.k_b = dp(p + "attention.self.key.weight"), dp(p + "attention.self.key.bias")
+            lw.v_w, lw.v_b = dp(p + "attention.self.value.weight"), dp(p + "attention.self.value.bias")
+            lw.ao_w, lw.ao_b = dp(p + "attention.output.dense.weight"), dp(p + "attention.output.dense.bias")
+            lw.ao_ln_g, lw.ao_ln_b = dp(p + "attention.output.LayerNorm.weight"), dp(p + "attention.output.LayerNorm.bias")
+            lw.ff1_w, lw.ff1_b = dp(p + "intermediate.dense.weight"), dp(p + "intermediate.dense.bias")
+            lw.ff2_w, lw.ff2_b = dp(p + "output.dense.weight"), dp(p + "output.dense.bias")
+            lw.out_ln_g, lw.out_ln_b = dp(p + "output.LayerNorm.weight"), dp(p + "output.LayerNorm.bias")
+        w = Weights()
+        w.word_emb = dp("bert.embeddings.word_embeddings.weight")
+        w.pos_emb = dp("bert.embeddings.position_embeddings.weight")
+        w.type_emb = dp("bert.embeddings.token_type_embeddings.weight")
+        w.emb_ln_g = dp("bert.embeddings.LayerNorm.weight")
+        w.emb_ln_b = dp("bert.embeddings.LayerNorm.bias")
+        w.layers = ctypes.cast(layers, ctypes.POINTER(LayerWeights))
+        w.head_w = dp("cls.predictions.transform.dense.weight")
+        w.head_b = dp("cls.predictions.transform.dense.bias")
+        w.head_ln_g = dp("cls.predictions.transform.LayerNorm.weight")
+        w.head_ln_b = dp("cls.predictions.transform.LayerNorm.bias")
+        dec_w = "cls.predictions.decoder.weight" if "cls.predictions.decoder.weight" in state_dict \
+            else "bert.embeddings.word_embeddings.weight"
+        w.decoder_w = dp(dec_w)
+        w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
+        d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
+                      self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id)
+        torch.cuda.synchronize(dev)
+        check(self._lib.pllb_create(ctypes.byref(self._h), ctypes.byref(d), ctypes.byref(w), int(max_chunk_tokens), device))
+        del keep   # the library made its own (bf16 / fp32) copies
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pllb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ scoring
+    @staticmethod
+    def _check_packed(tokens, offsets):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        if offsets.ndim != 1 or len(offsets) < 1:
+            raise ValueError("offsets must be a 1-D array of n_hyp+1 entries")
+        return offsets
+
+    def score_packed(self, tokens: np.ndarray, offsets: np.ndarray, return_token_logp: bool = False):
+        """HOST arrays in, HOST arrays out (H2D + score + D2H inside one C call).
+        tokens: int32 wordpiece ids of all hypotheses back to back (no specials);
+        offsets: int64[n_hyp+1].  Returns float64[n_hyp] PLLs (and float32 per-token terms)."""
+        offsets = self._check_packed(tokens, offsets)
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = len(offsets) - 1
+        out = np.zeros(n, np.float64)
+        tl = np.zeros(int(offsets[-1]), np.float32) if return_token_logp else None
+        check(self._lib.pllb_score_host(self._h, _np_ptr(tokens), _np_ptr(offsets), n, _np_ptr(out),
+                                        _np_ptr(tl) if tl is not None else None))
+        return (out, tl) if return_token_logp else out
+
+    def score_device(self, tokens_cuda, offsets: np.ndarray, out=None, token_logp=None):
+        """tokens_cuda: torch int32 CUDA tensor; offsets: host int64.  Asynchronous on the
+        current torch stream; returns a torch float64 CUDA tensor [n_hyp]."""
+        import torch
+        offsets = self._check_packed(None, offsets)
+        n = len(offsets) - 1
+        assert tokens_cuda.is_cuda and tokens_cuda.dtype == torch.int32 and tokens_cuda.is_contiguous()
+        if out is None:
+            out = torch.zeros(n, dtype=torch.float64, device=tokens_cuda.device)
+        stream = torch.cuda.current_stream(tokens_cuda.device).cuda_stream
+        check(self._lib.pllb_score(self._h, ctypes.c_void_p(tokens_cuda.data_ptr()), _np_ptr(offsets), n,
+                                   ctypes.c_void_p(out.data_ptr()),
+                                   ctypes.c_void_p(token_logp.data_ptr()) if token_logp is not None else None,
+                                   ctypes.c_void_p(stream)))
+        return out
+
+    def score_hyps(self, hyps: Dict[str, Dict[str, Sequence[int]]]) -> Dict[str, Dict[str, float]]:
+        """{utt: {hyp: [token ids]}} -> {utt: {hyp: PLL}}; a hypothesis with no tokens keeps
+        the int 0 of the reference's skeleton (MLM_PLL/main.py:189-193)."""
+        flat, off = [], [0]
+        for hs in hyps.values():
+            for toks in hs.values():
+                flat.extend(toks)
+                off.append(len(flat))
+        pll = self.score_packed(np.asarray(flat, np.int32), np.asarray(off, np.int64))
+        out, i = {}, 0
+        for u, hs in hyps.items():
+            out[u] = {}
+            for h, toks in hs.items():
+                out[u][h] = float(pll[i]) if len(toks) > 0 else 0
+                i += 1
+        return out
+
+    # ------------------------------------------------------------------ parity hooks
+    def expand(self, tokens: np.ndarray, offsets: np.ndarray):
+        import torch
+        offsets = self._check_packed(tokens, offsets)
+        L = np.diff(offsets)
+        dev = torch.device("cuda", self.device)
+        t = torch.from_numpy(np.ascontiguousarray(tokens, np.int32)).to(dev)
+        ids = torch.zeros(max(int((L * (L + 2)).sum()), 1), dtype=torch.int32, device=dev)
+        mp = torch.zeros(max(int(L.sum()), 1), dtype=torch.int32, device=dev)
+        lab = torch.zeros_like(mp)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(self._lib.pllb_expand(self._h, ctypes.c_void_p(t.data_ptr()), _np_ptr(offsets), len(L),
+                                    ctypes.c_void_p(ids.data_ptr()), ctypes.c_void_p(mp.data_ptr()),
+                                    ctypes.c_void_p(lab.data_ptr()), ctypes.c_void_p(stream)))
+        torch.cuda.synchronize(dev)
+        return (ids.cpu().numpy()[:int((L * (L + 2)).sum())], mp.cpu().numpy()[:int(L.sum())],
+                lab.cpu().numpy()[:int(L.sum())])
+
+    def hidden(self, tokens: np.ndarray, offsets: np.ndarray, upto_layer: int):
+        import torch
+        offsets = self._check_packed(tokens, offsets)
+        L = np.diff(offsets)
+        rows = int((L * (L + 2)).sum())
+        dev = torch.device("cuda", self.device)
+        t = torch.from_numpy(np.ascontiguousarray(tokens, np.int32)).to(dev)
+        out = torch.zeros(max(rows, 1), self.cfg["hidden"], dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        check(self._lib.pllb_debug_hidden(self._h, ctypes.c_void_p(t.data_ptr()), _np_ptr(offsets), len(L), upto_layer,
+                                          ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)))
+        torch.cuda.synchronize(dev)
+        return out[:rows].cpu()
+
+    # ------------------------------------------------------------------ stats
+    def set_timing(self, enable: bool):
+        check(self._lib.pllb_set_timing(self._h, int(enable)))
+
+    def reset_stats(self):
+        check(self._lib.pllb_reset_stats(self._h))
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(self._lib.pllb_get_stats(self._h, ctypes.byref(s)))
+        ms = (ctypes.c_float * 6)()
+        fl = (ctypes.c_double * 6)()
+        check(self._lib.pllb_get_gemm_breakdown(self._h, ms, fl))
+        d = {n: getattr(s, n) for n, _ in Stats._fields_}
+        d["gemm_ms_by_kind"] = dict(zip(GEMM_KINDS, [float(x) for x in ms]))
+        d["gemm_flops_by_kind"] = dict(zip(GEMM_KINDS, [float(x) for x in fl]))
+        d["workspace_bytes"] = int(self._lib.pllb_workspace_bytes(self._h))
+        return d
+
+
+# ---------------------------------------------------------------------- stage 4
+def pack_strings(strings: Sequence[str]):
+    off = np.zeros(len(strings) + 1, np.int64)
+    if len(strings):
+        np.cumsum([len(s) for s in strings], out=off[1:])
+    cp = np.fromiter((ord(c) for s in strings for c in s), np.int32, int(off[-1]))
+    return cp, off
+
+
+def levenshtein_packed(ref_cp, ref_off, hyp_cp, hyp_off, pair_ref) -> np.ndarray:
+    """Edit distances of (ref[pair_ref[i]], hyp[i]) pairs on the GPU (host arrays in/out)."""
+    lib = _lib.load()
+    _lib.require_device()
+    ref_cp = np.ascontiguousarray(ref_cp, np.int32)
+    hyp_cp = np.ascontiguousarray(hyp_cp, np.int32)
+    ref_off = np.ascontiguousarray(ref_off, np.int64)
+    hyp_off = np.ascontiguousarray(hyp_off, np.int64)
+    pair_ref = np.ascontiguousarray(pair_ref, np.int32)
+    out = np.zeros(len(pair_ref), np.int32)
+    check(lib.pllb_levenshtein_host(_np_ptr(ref_cp), _np_ptr(ref_off), len(ref_off) - 1, _np_ptr(hyp_cp),
+                                    _np_ptr(hyp_off), _np_ptr(pair_ref), len(pair_ref), _np_ptr(out)))
+    return out
+
+
+def levenshtein(refs: Sequence[str], hyps: Sequence[str], pair_ref: Optional[Sequence[int]] = None) -> np.ndarray:
+    """jiwer-style character edit distance: strings are stripped, characters = code points."""
+    refs = [r.strip() for r in refs]
+    hyps = [h.strip() for h in hyps]
+    rc, ro = pack_strings(refs)
+    hc, ho = pack_strings(hyps)
+    if pair_ref is None:
+        if len(refs) != len(hyps):
+            raise ValueError("reference and hypothesis lists differ in length")
+        pair_ref = np.arange(len(hyps), dtype=np.int32)
+    return levenshtein_packed(rc, ro, hc, ho, pair_ref)
+
+
+def rescore_sweep(am, lm, lens, dist, weights, variant="B"):
+    """For every weight: per-utterance argmax of the interpolated score and the summed edit
+    distance of the chosen hypotheses.  Returns (argmax int32 [W,N], edit_sum int64 [W])."""
+    lib = _lib.load()
+    _lib.require_device()
+    am = np.ascontiguousarray(am, np.float64)
+    lm = np.ascontiguousarray(lm, np.float64)
+    lens = np.ascontiguousarray(lens, np.int64)
+    weights = np.ascontiguousarray(weights, np.float64)
+    if am.shape != lm.shape or am.shape != lens.shape or am.ndim != 2:
+        raise ValueError(f"am {am.shape}, lm {lm.shape}, len {lens.shape} must be equal 2-D shapes")
+    N, nb = am.shape
+    W = len(weights)
+    arg = np.zeros((W, N), np.int32)
+    es = np.zeros(W, np.int64)
+    d = None
+    if dist is not None:
+        d = np.ascontiguousarray(dist, np.int32)
+        if d.shape != am.shape:
+            raise ValueError("dist shape mismatch")
+    check(lib.pllb_rescore_sweep_host(_np_ptr(am), _np_ptr(lm), _np_ptr(lens), _np_ptr(d) if d is not None else None,
+                                      N, nb, _np_ptr(weights), W, VARIANTS[variant], _np_ptr(arg), _np_ptr(es)))
+    return arg, es
+
+
+def rescore_scores(am, lm, lens, weight, variant="B") -> np.ndarray:
+    """The [N, n_best] interpolated score matrix for one weight (rescore.py:47-53)."""
+    import torch
+    lib = _lib.load()
+    _lib.require_device()
+    am = np.ascontiguousarray(am, np.float64)
+    lm = np.ascontiguousarray(lm, np.float64)
+    lens = np.ascontiguousarray(lens, np.int64)
+    if am.shape != lm.shape or am.shape != lens.shape or am.ndim != 2:
+        raise ValueError(f"am {am.shape}, lm {lm.shape}, len {lens.shape} must be equal 2-D shapes")
+    N, nb = am.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_am, d_lm, d_len = (torch.from_numpy(x).to(dev) for x in (am, lm, lens))
+    out = torch.empty(N, nb, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    check(lib.pllb_rescore_scores(ctypes.c_void_p(d_am.data_ptr()), ctypes.c_void_p(d_lm.data_ptr()),
+                                  ctypes.c_void_p(d_len.data_ptr()), N, nb, float(weight), VARIANTS[variant],
+                                  ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stream)))
+    torch.cuda.synchronize(dev)
+    return out.cpu().numpy()
+
+
+def debug_gemm(A_bf16, W_bf16, bias_f32, epilogue: int, simt: bool = False):
+    """Test hook: C = A @ W^T + bias through the tcgen05 (or SIMT validation) kernel."""
+    import torch
+    lib = _lib.load()
+    _lib.require_device()
+    M, K = A_bf16.shape
+    N = W_bf16.shape[0]
+    out = torch.empty(M, N, dtype=torch.bfloat16 if epilogue in (0, 1) else torch.float32, device=A_bf16.device)
+    stream = torch.cuda.current_stream(A_bf16.device).cuda_stream
+    fn = lib.pllb_debug_gemm_simt if simt else lib.pllb_debug_gemm
+    check(fn(ctypes.c_void_p(A_bf16.data_ptr()), ctypes.c_void_p(W_bf16.data_ptr()), ctypes.c_void_p(bias_f32.data_ptr()),
+             ctypes.c_void_p(out.data_ptr()), M, N, K, epilogue, ctypes.c_void_p(stream)))
+    return out
