@@ -1,0 +1,233 @@
+"""Drop-in for the scoring path of the reference's ``MLM_PLL/main.py``.
+
+    cd MLM_PLL && python main.py --config config/score.yaml
+
+Same ``--config`` flag, same YAML keys (MLM_PLL/config/score.yaml:1-20), same output files
+(``<output_path>{train,dev,test}_lm.json``: {utt_id: {hyp_id: float}}, indent=4,
+ensure_ascii=False).  Differences, each deliberate (SURVEY.md §8a "quirks"):
+
+* all three splits are scored — the reference's dev/test blocks sit inside a string
+  literal (MLM_PLL/main.py:205-238) although rescore.py consumes their outputs;
+* the arithmetic runs in libpllb200.so on a B200 (no padding, no [copies x T x V] logits,
+  no per-batch host syncs); there is no CPU fallback and ``task: training``
+  (MLM_PLL/main.py:117-161) is out of scope;
+* data files may be the reference's row-list JSON (MLM_PLL/preprocess.py:9-30), a
+  ``hyps_text.json`` ({utt: {hyp: str}}, tokenised here) or the compact packed JSON that
+  our ``preprocess.py`` writes — the O(sum L^2) row list is never needed;
+* optional keys (absent from the reference YAMLs, all defaulted): ``model.vocab_path``,
+  ``model.random_init_seed``, ``max_chunk_tokens``.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_PARENT = os.path.dirname(os.path.dirname(_HERE))
+if _PKG_PARENT not in sys.path:
+    sys.path.insert(0, _PKG_PARENT)
+
+from asr_rescoring_b200 import shard, synth  # noqa: E402
+from asr_rescoring_b200.engine import PllScorer  # noqa: E402
+from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer  # noqa: E402
+from asr_rescoring_b200.util.arg_parser import ArgParser  # noqa: E402
+from asr_rescoring_b200.util.saving import json_saving  # noqa: E402
+
+MODEL_SHAPES = {"bert-base-chinese": synth.BERT_BASE_CHINESE, "bert-large-shaped": synth.BERT_LARGE_SHAPED,
+                "bert-tiny-test": synth.BERT_TINY}
+
+
+class MyDataset:
+    """List wrapper with slice support — MLM_PLL/main.py:17-25."""
+
+    def __init__(self, data_set: List):
+        self.data_set = data_set
+
+    def __len__(self):
+        return len(self.data_set)
+
+    def __getitem__(self, idx):
+        return self.data_set[idx]
+
+
+def collate(batch: List[dict]):
+    """The reference pads rows into [B, Tmax] tensors here (MLM_PLL/main.py:28-54); the
+    varlen kernels need no padding, so a batch is just the list of rows."""
+    return list(batch)
+
+
+class RowLoader:
+    """Sequential batches of rows (shuffle=False as for scoring, MLM_PLL/main.py:58-61)."""
+
+    def __init__(self, dataset, batch_size: int):
+        self.dataset = dataset
+        self.batch_size = max(int(batch_size), 1)
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for s in range(0, len(self.dataset), self.batch_size):
+            yield collate(self.dataset[s:s + self.batch_size])
+
+
+def set_dataloader(config, dataset, for_scoring=False):
+    """MLM_PLL/main.py:57-70.  ``num_worker`` host processes are not needed (no tensors are
+    built on the host); the key is still read so a YAML without it fails as before."""
+    _ = config.num_worker
+    if not for_scoring:
+        raise NotImplementedError("only the scoring path (for_scoring=True) is implemented")
+    return RowLoader(dataset, config.batch_size)
+
+
+def _iter_rows(dataloader) -> Iterable[dict]:
+    for item in dataloader:
+        if isinstance(item, dict):
+            yield item
+        else:
+            for row in item:
+                yield row
+
+
+def run_one_epoch(config, model: PllScorer, dataloader, output_score=None, train_mode=True, do_scoring=False):
+    """Scoring branch of MLM_PLL/main.py:73-114: for every row (one masked copy) add
+    log_softmax(logits[mask_pos])[labels[mask_pos]] to output_score[utt_id][hyp_id].
+    Rows of one hypothesis are consecutive (preprocess.py emits them so); a row list cut in
+    the middle of a hypothesis by ``num_of_data`` adds only the rows present, like the
+    reference."""
+    if train_mode or not do_scoring:
+        raise NotImplementedError("MLM fine-tuning (MLM_PLL/main.py:96-99,117-161) is out of scope")
+    groups: List[Tuple[str, str, List[int], List[int]]] = []   # utt, hyp, tokens, mask positions present
+    last_key = None
+    for row in _iter_rows(dataloader):
+        key = (row["utt_id"], row["hyp_id"], tuple(row["labels"]))
+        if key != last_key:
+            groups.append((row["utt_id"], row["hyp_id"], list(row["labels"][1:-1]), []))
+            last_key = key
+        groups[-1][3].append(int(row["mask_pos"]) - 1)
+    if not groups:
+        return output_score
+    off = np.zeros(len(groups) + 1, np.int64)
+    np.cumsum([len(g[2]) for g in groups], out=off[1:])
+    tokens = np.fromiter((t for g in groups for t in g[2]), np.int32, int(off[-1]))
+    pll, tok_logp = model.score_packed(tokens, off, return_token_logp=True)
+    for i, (u, h, toks, present) in enumerate(groups):
+        if len(present) == len(toks) and present == list(range(len(toks))):
+            output_score[u][h] += float(pll[i])          # device sum, same order, in double
+        else:
+            for m in present:
+                output_score[u][h] += float(tok_logp[off[i] + m])
+    return output_score
+
+
+# ---------------------------------------------------------------------------- data
+def _tokenizer(config):
+    vocab_path = getattr(config.model, "vocab_path", None)
+    return BertCharTokenizer(vocab_path) if vocab_path else SyntheticCharTokenizer()
+
+
+def load_split(path: str, num_of_data: int, config) -> Tuple[Optional[list], Dict[str, Dict[str, List[int]]]]:
+    """Returns (rows or None, {utt: {hyp: token ids}}) for any of the three file formats."""
+    data = json.load(open(path, "r", encoding="utf-8"))
+    if isinstance(data, list):                       # reference row list
+        return data[:num_of_data], {}
+    if isinstance(data, dict) and data.get("format") == "pllb-packed-v1":
+        hyps: Dict[str, Dict[str, List[int]]] = {}
+        off, tok = data["offsets"], data["tokens"]
+        for i, (u, h) in enumerate(zip(data["utt_id"], data["hyp_id"])):
+            hyps.setdefault(u, {})[h] = tok[off[i]:off[i + 1]]
+        return None, hyps
+    tk = _tokenizer(config)                          # hyps_text.json
+    return None, {u: {h: tk.encode(s) for h, s in hs.items()} for u, hs in data.items()}
+
+
+def skeleton_from_rows(rows: list) -> dict:
+    """{utt: {hyp: 0}} exactly as MLM_PLL/main.py:189-193 (keys on hyp_id == "hyp_1")."""
+    out: dict = {}
+    for data in rows:
+        if data["hyp_id"] == "hyp_1":
+            out[data["utt_id"]] = {}
+        out[data["utt_id"]][data["hyp_id"]] = 0
+    return out
+
+
+def build_scorer(config, device: int = 0) -> PllScorer:
+    """Replaces BertForMaskedLM.from_pretrained + load_state_dict + .to(device)
+    (MLM_PLL/main.py:184-187): the checkpoint is the bare state_dict written by
+    util/saving.py:7-11; the model shape is inferred from it."""
+    import torch
+    seed = getattr(config.model, "random_init_seed", None)
+    ckpt = config.checkpoint_path
+    if ckpt and os.path.exists(ckpt):
+        sd = torch.load(ckpt, map_location="cpu")
+        cfg = synth.config_from_state_dict(sd)
+    elif seed is not None:
+        cfg = MODEL_SHAPES[config.model.bert]
+        sd = synth.random_init_state_dict(cfg, int(seed))
+    else:
+        raise FileNotFoundError(f"checkpoint_path {ckpt!r} not found and model.random_init_seed not set")
+    return PllScorer(sd, cfg, device=device, max_chunk_tokens=int(getattr(config, "max_chunk_tokens", 0) or 0))
+
+
+def score_split(config, model: PllScorer, path: str) -> dict:
+    rows, hyps = load_split(path, config.num_of_data, config)
+    rank, world, _ = shard.dist_env()
+    if rows is not None:
+        output_score = skeleton_from_rows(rows)
+        if world > 1:
+            raise NotImplementedError("row-list inputs are scored on one GPU; use hyps_text / packed JSON to shard")
+        loader = set_dataloader(config.dataloader, MyDataset(rows), True)
+        return run_one_epoch(config=config, model=model, dataloader=loader, output_score=output_score,
+                             train_mode=False, do_scoring=True)
+    utts = list(hyps.keys())
+    parts = shard.lpt_partition(shard.utterance_costs([[len(t) for t in hyps[u].values()] for u in utts]), world)
+    mine = [utts[i] for i in parts[rank]]
+    base = np.zeros(len(utts) + 1, np.int64)
+    np.cumsum([len(hyps[u]) for u in utts], out=base[1:])
+    local = model.score_hyps({u: hyps[u] for u in mine})
+    vals = np.array([float(v) for u in mine for v in local[u].values()], np.float64)
+    idx = np.array([base[i] + k for i in parts[rank] for k in range(len(hyps[utts[i]]))], np.int64)
+    full = shard.gather_scores(vals, idx, int(base[-1]))
+    out, j = {}, 0
+    for u in utts:
+        out[u] = {}
+        for h, toks in hyps[u].items():
+            out[u][h] = float(full[j]) if len(toks) > 0 else 0
+            j += 1
+    return out
+
+
+def pll_bert_scoring(config):
+    """MLM_PLL/main.py:164-203, for all three splits."""
+    rank, world, local = shard.init_process_group() if shard.dist_env()[1] > 1 else (0, 1, 0)
+    dev = config.device
+    device = local if world > 1 else (int(str(dev).split(":")[1]) if ":" in str(dev) else 0)
+    model = build_scorer(config, device)
+    for split, path in (("train", config.train_data_path), ("dev", config.dev_data_path), ("test", config.test_data_path)):
+        output_score = score_split(config, model, path)
+        if rank == 0:
+            json_saving(config.output_path + f"{split}_lm.json", output_score)   # string concat as main.py:203
+    model.close()
+
+
+def mlm_finetune_bert(config):
+    raise NotImplementedError("task 'training' (MLM_PLL/main.py:117-161) is out of scope of the B200 scoring path")
+
+
+if __name__ == "__main__":
+    arg_parser = ArgParser()
+    config = arg_parser.parse()
+
+    if config.seed is not None:
+        import torch
+        torch.manual_seed(config.seed)
+        torch.cuda.manual_seed(config.seed)
+
+    if config.task == "training":
+        mlm_finetune_bert(config)
+    elif config.task == "scoring":
+        pll_bert_scoring(config)

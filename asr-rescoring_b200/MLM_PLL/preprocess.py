@@ -1,0 +1,72 @@
+"""Drop-in for the ``for_scoring`` jobs of the reference's ``MLM_PLL/preprocess.py``.
+
+The reference materialises every masked copy as a JSON row (O(sum L^2) integers,
+MLM_PLL/preprocess.py:9-30); here the expansion happens on the GPU (stage 1 of
+libpllb200), so preprocessing only tokenises each hypothesis once and writes a compact
+packed file.  ``do_job`` is kept with the reference's signature and row schema for callers
+that still want rows (it is what the parity tests compare the device expansion against).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_PARENT = os.path.dirname(os.path.dirname(_HERE))
+if _PKG_PARENT not in sys.path:
+    sys.path.insert(0, _PKG_PARENT)
+
+from asr_rescoring_b200.synth import CLS_ID, MASK_ID, SEP_ID  # noqa: E402
+from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer  # noqa: E402
+from asr_rescoring_b200.util.saving import json_saving  # noqa: E402
+
+bert_tokenizer = None
+
+
+def _special(tokenizer, token, default):
+    vocab = getattr(tokenizer, "vocab", None)
+    return vocab.get(token, default) if vocab else default
+
+
+def do_job(sentence, utt_id, hyp_id, task_type, output_json, tokenizer=None):
+    """Row schema of MLM_PLL/preprocess.py:9-30 (one row per masked position)."""
+    tk = tokenizer or bert_tokenizer
+    ids = tk.encode(sentence)
+    cls_id, sep_id, mask_id = _special(tk, "[CLS]", CLS_ID), _special(tk, "[SEP]", SEP_ID), _special(tk, "[MASK]", MASK_ID)
+    for mask_pos in range(len(ids)):
+        output_json.append({
+            "utt_id": utt_id,
+            "hyp_id": hyp_id,
+            "input_ids": [cls_id] + ids[:mask_pos] + [mask_id] + ids[mask_pos + 1:] + [sep_id],
+            "attention_masks": [1] * (len(ids) + 2),
+            "mask_pos": mask_pos + 1,
+            "labels": [cls_id] + ids + [sep_id],
+        })
+    return output_json
+
+
+def pack_hyps_text(hyps_text: dict, tokenizer) -> dict:
+    """{utt: {hyp: str}} -> packed JSON consumed by main.py (format pllb-packed-v1)."""
+    utt, hyp, tokens, offsets = [], [], [], [0]
+    for utt_id, hyps in hyps_text.items():
+        for hyp_id, sentence in hyps.items():
+            utt.append(utt_id)
+            hyp.append(hyp_id)
+            tokens.extend(tokenizer.encode(sentence))
+            offsets.append(len(tokens))
+    return {"format": "pllb-packed-v1", "utt_id": utt, "hyp_id": hyp, "tokens": tokens, "offsets": offsets}
+
+
+if __name__ == "__main__":
+    vocab = os.environ.get("PLLB_VOCAB")   # path to bert-base-chinese vocab.txt when available
+    bert_tokenizer = BertCharTokenizer(vocab) if vocab else SyntheticCharTokenizer()
+    jobs = [
+        {"task": "for_scoring", "in": "../espnet_data/alfred/train/hyps_text.json", "out": "preprocessed_data/for_scoring/train.json"},
+        {"task": "for_scoring", "in": "../espnet_data/alfred/dev/hyps_text.json", "out": "preprocessed_data/for_scoring/dev.json"},
+        {"task": "for_scoring", "in": "../espnet_data/alfred/test/hyps_text.json", "out": "preprocessed_data/for_scoring/test.json"},
+    ]
+    for job in jobs:
+        json_data = json.load(open(job["in"], "r", encoding="utf-8"))
+        os.makedirs(os.path.dirname(job["out"]), exist_ok=True)
+        json_saving(job["out"], pack_hyps_text(json_data, bert_tokenizer))

@@ -1,0 +1,299 @@
+"""Parity of the CUDA path (through the C ABI of libpllb200.so) against the oracle and the
+committed golden fixtures.  Integer / byte / fp64 work: bit-exact.  PLL: within 0.05 nats
+absolute per hypothesis (north_star: bf16 operands, fp32 accumulate)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import pll_oracle, rescore_oracle
+from asr_rescoring_b200 import engine, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("require_gpu")]
+
+PLL_TOL = 0.05   # nats, absolute, per hypothesis (BASELINE.json north_star)
+
+
+# ----------------------------------------------------------------------------- stage 4
+def test_levenshtein_reference_kats_bit_exact(gold_dir):
+    z = np.load(os.path.join(gold_dir, "levenshtein_kat.npz"))
+    got = engine.levenshtein_packed(z["ref_cp"], z["ref_off"], z["hyp_cp"], z["hyp_off"],
+                                    np.arange(len(z["dist"]), dtype=np.int32))
+    assert np.array_equal(got, z["dist"])           # Nbest_Align/cer.json, 7 176 pairs
+    assert int(got.sum()) == 3230
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 63, 64, 65, 128, 129, 300, 513, 1024])
+def test_levenshtein_lengths_and_edge_cases(n):
+    rng = np.random.default_rng(n)
+    mk = lambda k: "".join(chr(0x4E00 + int(c)) for c in rng.integers(0, 12, size=k))
+    refs = [mk(max(n + int(rng.integers(-5, 6)), 0)) for _ in range(40)] + ["", mk(n), mk(3)]
+    hyps = [mk(n) for _ in range(40)] + [mk(n), "", ""]
+    hyps[0] = refs[0][:1024]
+    assert np.array_equal(engine.levenshtein(refs, hyps), oracle.levenshtein_strings(refs, hyps))
+
+
+def test_levenshtein_rejects_too_long():
+    from asr_rescoring_b200._lib import PllbError
+    with pytest.raises(PllbError):
+        engine.levenshtein(["a"], ["b" * 1025])
+
+
+def test_levenshtein_pair_ref_and_strip():
+    refs = ["你好嗎", "how are you"]
+    hyps = ["你好不好", " 你好嗎 ", "how are you doing", "haw are you"]
+    got = engine.levenshtein(refs, hyps, pair_ref=[0, 0, 1, 1])
+    assert got.tolist() == [2, 0, 6, 1]             # align.py:13-18 example 2 has distance 2
+
+
+def _bits_equal(a, b):
+    return bool(((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+def test_combiner_bit_exact_vs_reference_golden(gold_dir):
+    z = np.load(os.path.join(gold_dir, "combiner_golden.npz"))
+    N, nb = z["am"].shape
+    pair_ref = np.repeat(np.arange(N, dtype=np.int32), nb)
+    dist = engine.levenshtein_packed(z["ref_cp"], z["ref_off"], z["hyp_cp"], z["hyp_off"], pair_ref).reshape(N, nb)
+    assert np.array_equal(dist, oracle.levenshtein_batch(z["ref_cp"], z["ref_off"], z["hyp_cp"], z["hyp_off"], pair_ref).reshape(N, nb))
+    arg, es = engine.rescore_sweep(z["am"], z["lm"], z["lens"], dist, z["weights"], "B")
+    assert np.array_equal(arg, z["argmax"])         # rescore.py outputs, incl. tie and NaN rows
+    for i, wi in enumerate(z["score_idx"]):
+        s = engine.rescore_scores(z["am"], z["lm"], z["lens"], z["weights"][wi], "B")
+        assert _bits_equal(s, z["scores"][i])
+    cers = es / float(z["ref_off"][-1])
+    assert z["weights"][int(np.argmin(cers))] == float(z["best_weight"]) and cers.min() == float(z["best_cer"])
+
+
+@pytest.mark.parametrize("variant,code", [("B", 0), ("A", 1), ("C", 2)])
+def test_combiner_variants_vs_oracle(variant, code):
+    nb = synth.make_nbest(400, 7, seed=21)
+    lm = synth.synthetic_lm_scores(nb, seed=5)
+    lens = np.array([[len(h) for h in hs] for hs in nb.hyps], np.int64)
+    lens[3, 2] = 0                                   # len == 0 -> inf / nan semantics (rescore.py:51)
+    rng = np.random.default_rng(0)
+    dist = rng.integers(0, 9, size=lens.shape).astype(np.int32)
+    w = np.arange(0.0, 1.01, 0.01)
+    arg, es = engine.rescore_sweep(nb.am, lm, lens, dist, w, variant)
+    arg_o, es_o = oracle.rescore_sweep(nb.am, lm, lens, dist, w, code)
+    assert np.array_equal(arg, arg_o) and np.array_equal(es, es_o)
+    with np.errstate(all="ignore"):
+        s_np = rescore_oracle.rescore(w[29], lens, nb.am, lm, rescore_oracle.config(7), variant)
+    assert _bits_equal(engine.rescore_scores(nb.am, lm, lens, w[29], variant), s_np)
+
+
+def test_drop_in_rescore_functions_match_oracle():
+    from asr_rescoring_b200 import rescore as dropin
+    nb = synth.make_nbest(200, 10, seed=33)
+    lm = synth.synthetic_lm_scores(nb, seed=6)
+    cfg = rescore_oracle.config(6)                   # n_best < available: am is sliced, lm pre-sliced (rescore.py:48-49)
+    lm6 = [r[:6] for r in lm.tolist()]
+    bw, bc = dropin.find_best_weight(nb.am.tolist(), lm6, nb.hyps, nb.refs, cfg)
+    bw_o, bc_o = rescore_oracle.find_best_weight(nb.am.tolist(), lm6, nb.hyps, nb.refs, cfg)
+    assert bw == bw_o and bc == bc_o
+    lens = dropin._hyps_len(nb.hyps, 6)
+    s = dropin.rescore(bw, lens, nb.am.tolist(), lm6, cfg)
+    assert _bits_equal(s, rescore_oracle.rescore(bw_o, lens, nb.am.tolist(), lm6, cfg))
+    assert dropin.get_highest_score_hyp(s, nb.hyps) == rescore_oracle.get_highest_score_hyp(s, nb.hyps)
+    assert dropin.cer(nb.refs, [h[0] for h in nb.hyps]) == rescore_oracle.cer(nb.refs, [h[0] for h in nb.hyps])
+    with pytest.raises(ValueError):
+        dropin.cer([""], ["a"])
+
+
+def test_combiner_full_size_properties():
+    """Config 5 size (7 176 x 50-best, 101 weights): size-independent properties."""
+    nb = synth.make_nbest(7176, 50, seed=9)
+    lm = synth.synthetic_lm_scores(nb, seed=3)
+    lens = np.array([[len(h) for h in hs] for hs in nb.hyps], np.int64)
+    from asr_rescoring_b200 import rescore as dropin
+    dist = dropin.pair_distances(nb.hyps, nb.refs, 50)
+    assert dist.shape == (7176, 50)
+    # bounded by the number of random edits applied; 0 iff strings equal
+    assert (dist <= nb.edits).all()
+    same = np.array([[h == r for h in hs] for hs, r in zip(nb.hyps, nb.refs)])
+    assert ((dist == 0) == same).all()
+    w = np.arange(0.0, 1.01, 0.01)
+    arg, es = engine.rescore_sweep(nb.am, lm, lens, dist, w, "B")
+    # weight 0 -> argmax of am/len; weight 1 (last grid point is 1.0) -> argmax of lm/len
+    assert np.array_equal(arg[0], np.argmax(nb.am / lens, axis=1))
+    assert w[-1] == 1.0 and np.array_equal(arg[-1], np.argmax((1 - w[-1]) * nb.am / lens + w[-1] * lm / lens, axis=1))
+    # checksum of checksums: edit sums equal the gathered distances, any order
+    assert np.array_equal(es, np.take_along_axis(dist, arg.T.astype(np.int64), axis=1).sum(0))
+    # sample of rows against the C oracle
+    rows = np.arange(0, 7176, 97)
+    arg_o, _ = oracle.rescore_sweep(nb.am[rows], lm[rows], lens[rows], dist[rows], w, 0)
+    assert np.array_equal(arg[:, rows], arg_o)
+
+
+# ----------------------------------------------------------------------------- stage 1
+def test_expansion_matches_reference_rows():
+    sd = synth.random_init_state_dict(synth.BERT_TINY, 1)
+    with engine.PllScorer(sd, synth.BERT_TINY) as sc:
+        nb = synth.make_nbest(30, 6, seed=1)
+        nb.hyps[0][0] = ""                           # empty hypothesis -> no rows
+        nb.hyps[2][3] = nb.hyps[2][3][:1]            # single token
+        tok, off = nb.packed_tokens(synth.BERT_TINY["vocab"])
+        ids, mp, lab = sc.expand(tok, off)
+        ids_o, mp_o, lab_o = oracle.expand(tok, off)
+        assert np.array_equal(ids, ids_o) and np.array_equal(mp, mp_o) and np.array_equal(lab, lab_o)
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 256, 64), (127, 256, 64), (128, 512, 128), (300, 768, 768), (1000, 2304, 768),
+                                   (2049, 3072, 768), (513, 768, 3072), (700, 1024, 1024)])
+def test_tcgen05_gemm_vs_fp32_torch(M, N, K):
+    import torch
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = A.float() @ W.float().T + b              # plain PyTorch fp32 reference of the same op
+    for epi in (2, 3, 0, 1):
+        out = engine.debug_gemm(A, W, b, epi).float()
+        r = torch.nn.functional.gelu(ref) if epi in (1, 3) else ref
+        if epi >= 2:
+            assert (out - r).abs().max().item() < 1e-3
+        else:                                        # bf16 output: half an ulp of the value
+            assert ((out - r).abs() <= r.abs() * 2 ** -8 + 1e-3).all()
+        simt = engine.debug_gemm(A, W, b, epi, simt=True).float()
+        assert (out - simt).abs().max().item() < (1e-3 if epi >= 2 else 0.07)
+
+
+# ----------------------------------------------------------------------------- encoder / PLL
+def _oracle_hidden(sd, cfg, tok, off, upto):
+    import torch
+    out = []
+    for h in range(len(off) - 1):
+        toks = [int(t) for t in tok[off[h]:off[h + 1]]]
+        for r in pll_oracle.expand_rows(toks, "u", "h"):
+            ids = torch.tensor([r["input_ids"]])
+            out.append(pll_oracle.bert_mlm_logits(sd, cfg, ids, torch.ones_like(ids), upto_layer=upto, return_hidden=True)[0])
+    return torch.cat(out)
+
+
+def test_embeddings_and_layers_vs_oracle():
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 10, perturb=True)
+    nb = synth.make_nbest(4, 3, seed=2)
+    tok, off = nb.packed_tokens(cfg["vocab"])
+    with engine.PllScorer(sd, cfg) as sc:
+        e0 = (sc.hidden(tok, off, 0) - _oracle_hidden(sd, cfg, tok, off, 0)).abs().max().item()
+        assert e0 < 5e-6                              # fp32 embedding + LayerNorm
+        for upto in (1, 2):
+            err = (sc.hidden(tok, off, upto) - _oracle_hidden(sd, cfg, tok, off, upto)).abs()
+            assert err.max().item() < 0.03 and err.mean().item() < 3e-3   # bf16 GEMM operands
+
+
+def test_pll_vs_reference_golden(gold_dir):
+    gold = json.load(open(os.path.join(gold_dir, "pll_golden.json")))
+    for case in gold["cases"]:
+        sd = synth.random_init_state_dict(case["cfg"], case["seed"], case["perturb"])
+        with engine.PllScorer(sd, case["cfg"]) as sc:
+            got = sc.score_hyps(case["hyps"])
+        for u, hs in case["pll"].items():
+            for h, v in hs.items():
+                assert abs(got[u][h] - v) <= PLL_TOL, (case["name"], u, h, got[u][h], v)
+                if len(case["hyps"][u][h]) == 0:
+                    assert got[u][h] == 0 and isinstance(got[u][h], int)
+
+
+def test_pll_vs_live_oracle_and_rescored_one_best():
+    cfg = synth.BERT_BASE_CHINESE
+    sd = synth.random_init_state_dict(cfg, 10)
+    nb = synth.make_nbest(12, 5, seed=77)
+    tok, off = nb.packed_tokens()
+    hyps, i = {}, 0
+    for u, hs in zip(nb.utt_ids, nb.hyps):
+        hyps[u] = {}
+        for k in range(len(hs)):
+            hyps[u][f"hyp_{k + 1}"] = [int(t) for t in tok[off[i]:off[i + 1]]]
+            i += 1
+    exp = pll_oracle.score_hyps(sd, cfg, hyps)
+    with engine.PllScorer(sd, cfg) as sc:
+        got = sc.score_hyps(hyps)
+        pll, tl = sc.score_packed(tok, off, return_token_logp=True)
+    d = np.array([got[u][h] - exp[u][h] for u in hyps for h in hyps[u]])
+    assert np.abs(d).max() <= PLL_TOL, np.abs(d).max()
+    # sum of the per-token terms (fp32) in order, in double, is the PLL (MLM_PLL/main.py:105-107)
+    for j in range(len(off) - 1):
+        assert pll[j] == float(np.sum(tl[off[j]:off[j + 1]].astype(np.float64)))
+    # rescored 1-best at the weight the oracle picks
+    lm_g = np.array([[got[u][h] for h in hyps[u]] for u in hyps])
+    lm_o = np.array([[exp[u][h] for h in hyps[u]] for u in hyps])
+    c = rescore_oracle.config(5)
+    bw, _ = rescore_oracle.find_best_weight(nb.am.tolist(), lm_o.tolist(), nb.hyps, nb.refs, c)
+    lens = rescore_oracle.hyps_len_of(nb.hyps, 5)
+    a_o = np.argmax(rescore_oracle.rescore(bw, lens, nb.am, lm_o, c), -1)
+    a_g = np.argmax(rescore_oracle.rescore(bw, lens, nb.am, lm_g, c), -1)
+    assert (a_o == a_g).mean() >= 0.9
+
+
+def test_scoring_is_deterministic_and_chunking_invariant():
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 4, perturb=True)
+    nb = synth.make_nbest(60, 5, seed=8)
+    nb.hyps[5][1] = ""
+    tok, off = nb.packed_tokens(cfg["vocab"])
+    with engine.PllScorer(sd, cfg) as big, engine.PllScorer(sd, cfg, max_chunk_tokens=2048) as small:
+        a, ta = big.score_packed(tok, off, return_token_logp=True)
+        b = big.score_packed(tok, off)
+        c, tc = small.score_packed(tok, off, return_token_logp=True)
+        assert small.stats()["chunks"] > 5 and big.stats()["chunks"] == 2
+    assert np.array_equal(a, b)                       # run twice: bitwise identical
+    assert np.array_equal(a, c) and np.array_equal(ta, tc)   # any chunking: bitwise identical
+    empty = np.diff(off) == 0
+    assert (a[empty] == 0.0).all() and np.isfinite(a).all()
+
+
+def test_duplicate_hypotheses_score_identically_at_scale():
+    """Size-independent property at a multi-chunk size: a hypothesis' PLL does not depend on
+    its neighbours or its position in the packed batch."""
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 5)
+    nb = synth.make_nbest(400, 10, seed=12)
+    tok, off = nb.packed_tokens(cfg["vocab"])
+    L = np.diff(off)
+    perm = np.random.default_rng(0).permutation(len(L))
+    tok_p = np.concatenate([tok[off[i]:off[i + 1]] for i in perm])
+    off_p = np.zeros(len(L) + 1, np.int64)
+    np.cumsum(L[perm], out=off_p[1:])
+    with engine.PllScorer(sd, cfg, max_chunk_tokens=1 << 16) as sc:
+        a = sc.score_packed(tok, off)
+        b = sc.score_packed(tok_p, off_p)
+    assert np.array_equal(a[perm], b)
+
+
+def test_too_long_hypothesis_is_rejected():
+    from asr_rescoring_b200._lib import PllbError
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 5)
+    with engine.PllScorer(sd, cfg) as sc:
+        n = cfg["max_position"] - 1                  # needs n + 2 positions
+        with pytest.raises(PllbError):
+            sc.score_packed(np.full(n, 700, np.int32), np.array([0, n], np.int64))
+
+
+def test_drop_in_run_one_epoch_matches_oracle_rows():
+    from asr_rescoring_b200.MLM_PLL import main as dropin
+    from types import SimpleNamespace
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 10, perturb=True)
+    nb = synth.make_nbest(5, 3, seed=14)
+    tok, off = nb.packed_tokens(cfg["vocab"])
+    rows, i = [], 0
+    for u, hs in zip(nb.utt_ids, nb.hyps):
+        for k in range(len(hs)):
+            rows += pll_oracle.expand_rows([int(t) for t in tok[off[i]:off[i + 1]]], u, f"hyp_{k + 1}")
+            i += 1
+    rows = rows[:len(rows) - 3]                      # num_of_data cuts the last hypothesis short
+    skel = dropin.skeleton_from_rows(rows)
+    exp = pll_oracle.score_rows(sd, cfg, rows, {u: dict(v) for u, v in skel.items()})
+    with engine.PllScorer(sd, cfg) as sc:
+        loader = dropin.set_dataloader(SimpleNamespace(batch_size=32, num_worker=5), dropin.MyDataset(rows), True)
+        got = dropin.run_one_epoch(config=SimpleNamespace(device="cuda:0"), model=sc, dataloader=loader,
+                                   output_score=skel, train_mode=False, do_scoring=True)
+    for u in exp:
+        for h in exp[u]:
+            assert abs(got[u][h] - exp[u][h]) <= PLL_TOL

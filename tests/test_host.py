@@ -1,0 +1,156 @@
+"""Host-side logic (CPU): synthetic data, config/CLI surface, tokenizer, sharding and the
+world-size-2 gloo path of the score gather / count reduce."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from asr_rescoring_b200 import shard, synth
+from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer
+from asr_rescoring_b200.util.arg_parser import ArgParser
+from asr_rescoring_b200.util.config import parse_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synth_is_deterministic_and_aishell_shaped():
+    a, b = synth.make_nbest(50, 10, seed=0), synth.make_nbest(50, 10, seed=0)
+    assert a.hyps == b.hyps and np.array_equal(a.am, b.am)
+    assert (np.diff(a.am, axis=1) <= 0).all()              # AM scores sorted descending
+    assert all(len(h) >= 1 for hs in a.hyps for h in hs)
+    tok, off = a.packed_tokens()
+    assert tok.min() >= 670 and tok.max() < 670 + 7322 and len(off) == 501
+    full = synth._length_pool()
+    assert len(full) == 7176 and int(full.sum()) == 104765  # espnet_data/alfred/test/ref_text.json
+
+
+def test_random_init_keys_match_hf_state_dict_names():
+    sd = synth.random_init_state_dict(synth.BERT_TINY, 3)
+    assert sd["cls.predictions.decoder.weight"] is sd["bert.embeddings.word_embeddings.weight"]
+    assert float(sd["bert.embeddings.word_embeddings.weight"][0].abs().sum()) == 0.0
+    assert synth.config_from_state_dict(sd)["num_layers"] == 2
+    try:
+        from transformers import BertConfig, BertForMaskedLM
+    except Exception:
+        pytest.skip("transformers not importable")
+    c = synth.BERT_TINY
+    hf = BertForMaskedLM(BertConfig(vocab_size=c["vocab"], hidden_size=c["hidden"], num_hidden_layers=c["num_layers"],
+                                    num_attention_heads=c["num_heads"], intermediate_size=c["intermediate"],
+                                    max_position_embeddings=c["max_position"]))
+    hf_keys = {k for k in hf.state_dict() if "position_ids" not in k}
+    assert hf_keys == set(sd.keys())
+
+
+def test_config_surface(tmp_path):
+    p = tmp_path / "c.yaml"
+    p.write_text(open(os.path.join(ROOT, "asr-rescoring_b200", "MLM_PLL", "config", "score.yaml")).read())
+    cfg = ArgParser().parse(["--config", str(p)])
+    assert cfg.task == "scoring" and cfg.seed == 10 and cfg.dataloader.batch_size == 32 and cfg.model.bert == "bert-base-chinese"
+    with pytest.raises(AttributeError):     # the reference's only error convention
+        _ = cfg.missing_key
+    assert parse_config({"a": {"b": 1}}).a.b == 1
+    with pytest.raises(SystemExit):
+        ArgParser().parse([])
+
+
+def test_tokenizer_matches_transformers_bert_tokenizer(tmp_path):
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "你", "好", "嗎", "a", "ab", "##c", "##d", "hello", "1", "##2", ",", "。"]
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    mine = BertCharTokenizer(str(vp))
+    texts = ["你好嗎", "你好 abc Hello,12。", "未知字 abcd xyz", "  你  好 ", "ABD", ""]
+    try:
+        from transformers import BertTokenizer
+        hf = BertTokenizer(str(vp))
+    except Exception:
+        hf = None
+    for t in texts:
+        toks = mine.tokenize(t)
+        if hf is not None:
+            assert toks == hf.tokenize(t), t
+            assert mine.convert_tokens_to_ids(toks) == hf.convert_tokens_to_ids(toks)
+    assert mine.tokenize("你好abc") == ["你", "好", "ab", "##c"]
+    assert SyntheticCharTokenizer().encode("你好") == [synth.synthetic_token_id("你"), synth.synthetic_token_id("好")]
+
+
+def test_lpt_partition_is_balanced_and_deterministic():
+    rng = np.random.default_rng(0)
+    lens = [[int(x) for x in rng.integers(3, 38, size=10)] for _ in range(500)]
+    costs = shard.utterance_costs(lens)
+    for world in (1, 2, 4, 8):
+        parts = shard.lpt_partition(costs, world)
+        allidx = np.sort(np.concatenate(parts))
+        assert np.array_equal(allidx, np.arange(500))
+        loads = np.array([costs[p].sum() for p in parts])
+        assert loads.max() <= loads.mean() * 1.02 + costs.max()
+        again = shard.lpt_partition(costs, world)
+        assert all(np.array_equal(a, b) for a, b in zip(parts, again))
+
+
+def test_drop_in_function_surface():
+    import importlib
+    m = importlib.import_module("asr_rescoring_b200.MLM_PLL.main")
+    r = importlib.import_module("asr_rescoring_b200.rescore")
+    for name in ("MyDataset", "collate", "set_dataloader", "run_one_epoch", "pll_bert_scoring", "mlm_finetune_bert"):
+        assert hasattr(m, name)
+    for name in ("dict_to_list", "find_best_weight", "rescore", "get_highest_score_hyp", "cer"):
+        assert hasattr(r, name)
+    assert r.dict_to_list({"u1": {"hyp_1": 1.0, "hyp_2": 2.0}, "u2": "abc"}) == [[1.0, 2.0], "abc"]
+    assert r.get_highest_score_hyp(np.array([[0.1, 0.3, 0.3], [np.nan, 1.0, 2.0]]), [["a", "b", "c"], ["d", "e", "f"]]) == ["b", "d"]
+    rows = [{"utt_id": "u", "hyp_id": "hyp_1"}, {"utt_id": "u", "hyp_id": "hyp_2"}, {"utt_id": "v", "hyp_id": "hyp_1"}]
+    assert m.skeleton_from_rows(rows) == {"u": {"hyp_1": 0, "hyp_2": 0}, "v": {"hyp_1": 0}}
+    with pytest.raises(KeyError):            # quirk 3: no hyp_1 row for an utterance
+        m.skeleton_from_rows([{"utt_id": "w", "hyp_id": "hyp_2"}])
+    with pytest.raises(NotImplementedError):
+        m.run_one_epoch(None, None, [], {}, train_mode=True)
+
+
+def test_preprocess_rows_match_reference_schema():
+    import importlib
+    p = importlib.import_module("asr_rescoring_b200.MLM_PLL.preprocess")
+    from oracle import pll_oracle
+    tk = SyntheticCharTokenizer()
+    rows = p.do_job("你好嗎", "utt", "hyp_1", "for_scoring", [], tokenizer=tk)
+    assert rows == pll_oracle.expand_rows(tk.encode("你好嗎"), "utt", "hyp_1")
+    packed = p.pack_hyps_text({"u": {"hyp_1": "你好", "hyp_2": ""}}, tk)
+    assert packed["offsets"] == [0, 2, 2] and packed["format"] == "pllb-packed-v1"
+
+
+GLOO_WORKER = textwrap.dedent("""
+    import os, sys, json
+    import numpy as np
+    sys.path.insert(0, os.environ["PLLB_ROOT"])
+    import torch.distributed as dist
+    from asr_rescoring_b200 import shard
+    rank, world, _ = shard.init_process_group(backend="gloo")
+    rng = np.random.default_rng(0)
+    lens = [[int(x) for x in rng.integers(1, 30, size=4)] for _ in range(37)]
+    parts = shard.lpt_partition(shard.utterance_costs(lens), world)
+    base = np.arange(0, 37 * 4 + 1, 4)
+    # stand-in per-hypothesis "scores": a deterministic function of the global hypothesis index
+    idx = np.array([base[u] + k for u in parts[rank] for k in range(4)], np.int64)
+    vals = -np.sqrt(idx.astype(np.float64) + 1.0) * 3.3
+    full = shard.gather_scores(vals, idx, 37 * 4)
+    counts = shard.reduce_counts(np.array([len(idx), int(idx.sum())], np.int64))
+    if rank == 0:
+        print(json.dumps({"ok": bool(np.array_equal(full, -np.sqrt(np.arange(148) + 1.0) * 3.3)),
+                          "counts": counts.tolist()}))
+    dist.destroy_process_group()
+""")
+
+
+def test_gloo_world_size_2_gather_and_reduce(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, PLLB_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["ok"] and res["counts"] == [148, sum(range(148))]
