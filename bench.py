@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--utts", type=int, default=0, help="override the number of utterances (debug)")
     ap.add_argument("--chunk-tokens", type=int, default=1 << 20)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-sample-hyps", type=int, default=40, help="hypotheses in the bounded CPU sample")
+    ap.add_argument("--cpu-sample-hyps", type=int, default=400, help="hypotheses in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -89,10 +89,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -100,10 +100,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.splitlines()[0].split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
