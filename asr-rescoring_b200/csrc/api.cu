@@ -67,7 +67,7 @@ struct pllb_context {
   __nv_bfloat16 *hidden_bf16 = nullptr, *wide = nullptr /* qkv [rows,3H] or ffn [rows,I] */, *ctx = nullptr;
   CopyPlan plan{};
   __nv_bfloat16 *hg = nullptr, *t_bf16 = nullptr;
-  float *t_f32 = nullptr, *label_logit = nullptr, *tok_logp = nullptr;
+  float *t_f32 = nullptr, *hid_c = nullptr, *label_logit = nullptr, *tok_logp = nullptr;
   float2* partials = nullptr;
   // per-call hypothesis metadata (grown on demand)
   int32_t* meta_dev = nullptr;
@@ -139,7 +139,7 @@ int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const fl
   }
   RC(launch_gemm_tcgen05(A, W, bias, C, M, N, K, epi, lse, s));
   if (tl) PLLB_CUDA(cudaEventRecord(tl->stop, s));
-  const double fl = 2.0 * (double)M * (double)N * (double)K;
+  const double fl = 2.0 * (double)M * (double)(epi == EPI_LSE && lse ? lse->vocab : N) * (double)K;
   c->stats.gemm_flops += fl;
   c->gemm_flops_kind[kind] += fl;
   c->stats.last_gemm_launches += 1;
@@ -157,10 +157,25 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
                      d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->hidden_f32, c->hidden_bf16, s));
   const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
+  // Only the [MASK] row of each copy reaches the MLM head (MLM_PLL/main.py:101), and after the
+  // last layer's attention every remaining op is row-wise: the last layer's output
+  // projection, LayerNorms and FFN run on the gathered masked rows only (1 row per copy
+  // instead of T).  Results are identical; the reference computes and discards the rest.
+  const bool prune_last = upto_layer < 0 && n_layers > 0;
   for (int l = 0; l < n_layers; ++l) {
     const LayerDev& L = c->layers[l];
     RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide, n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
     RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, s));
+    if (prune_last && l == n_layers - 1) {
+      RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
+      RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
+      RC(timed_gemm(c, G_AO, c->hg, L.ao_w, L.ao_b, c->y_f32, n_copies, H, H, EPI_BIAS_F32, nullptr, s));
+      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.ao_g, L.ao_be, d.ln_eps, n_copies, H, s));
+      RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
+      RC(timed_gemm(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, c->y_f32, n_copies, H, I, EPI_BIAS_F32, nullptr, s));
+      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.out_g, L.out_be, d.ln_eps, n_copies, H, s));
+      break;
+    }
     RC(timed_gemm(c, G_AO, c->ctx, L.ao_w, L.ao_b, c->y_f32, n_rows, H, H, EPI_BIAS_F32, nullptr, s));
     RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.ao_g, L.ao_be, d.ln_eps, n_rows, H, s));
     RC(timed_gemm(c, G_FF1, c->hidden_bf16, L.ff1_w, L.ff1_b, c->wide, n_rows, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
@@ -170,12 +185,12 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   if (upto_layer >= 0) return PLLB_OK;
   // MLM head at the masked row of every copy only (the reference evaluates all B*T rows,
   // transformers modeling_bert.py:975, and keeps one: MLM_PLL/main.py:101).
-  RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->hg, s));
-  RC(timed_gemm(c, G_HEAD, c->hg, c->head_w, c->head_b, c->t_f32, n_copies, H, H, EPI_BIAS_GELU_F32, nullptr, s));
-  RC(launch_plain_ln_bf16(c->t_f32, c->t_bf16, c->head_g, c->head_be, d.ln_eps, n_copies, H, s));
+  if (!prune_last) RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->t_bf16, s));
+  RC(timed_gemm(c, G_HEAD, c->t_bf16, c->head_w, c->head_b, c->t_f32, n_copies, H, H, EPI_BIAS_GELU_F32, nullptr, s));
+  RC(launch_plain_ln_bf16(c->t_f32, c->hg, c->head_g, c->head_be, d.ln_eps, n_copies, H, s));
   LseArgs lse{c->plan.label, c->partials, c->label_logit, d.vocab};
-  RC(timed_gemm(c, G_DEC, c->t_bf16, c->dec_w, c->dec_b, nullptr, n_copies, c->vocab_pad, H, EPI_LSE, &lse, s));
-  RC(launch_lse_finish(c->partials, c->label_logit, n_copies, c->tiles_v, c->tok_logp, s));
+  RC(timed_gemm(c, G_DEC, c->hg, c->dec_w, c->dec_b, nullptr, n_copies, c->vocab_pad, H, EPI_LSE, &lse, s));
+  RC(launch_lse_finish(c->partials, c->label_logit, n_copies, 2 * c->tiles_v, c->tok_logp, s));
   RC(launch_hyp_sum(c->tok_logp, copy_base, n_hyp, out_pll, out_tok_logp, s));
   return PLLB_OK;
 }
@@ -415,8 +430,9 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   TRY(dev_alloc(c, &c->plan.hyp, C));
   TRY(dev_alloc(c, &c->hg, C * H));
   TRY(dev_alloc(c, &c->t_f32, C * H));
+  TRY(dev_alloc(c, &c->hid_c, C * H));
   TRY(dev_alloc(c, &c->t_bf16, C * H));
-  TRY(dev_alloc(c, &c->partials, C * c->tiles_v));
+  TRY(dev_alloc(c, &c->partials, C * c->tiles_v * 2));
   TRY(dev_alloc(c, &c->label_logit, C));
   TRY(dev_alloc(c, &c->tok_logp, C));
 #undef TRY

@@ -46,7 +46,7 @@ enum GemmEpilogue : int {
 
 struct LseArgs {
   const int32_t* labels;   // [M] label column of each row
-  float2* partials;        // [M, n_tiles_n] (running max, sum of exp) per vocab tile
+  float2* partials;        // [M, 2 * n_tiles_n] (running max, sum of exp) per 128-column half tile
   float* label_logit;      // [M] written by the tile that owns the label column
   int32_t vocab;           // real vocab size (columns >= vocab are masked)
 };
@@ -84,8 +84,11 @@ int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const f
                          int H, cudaStream_t s);
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
                      int max_T, cudaStream_t s);
+int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
+                          int max_T, cudaStream_t s);
 int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out,
                             cudaStream_t s);
+int launch_gather_rows_f32(const float* src, const int32_t* rows, int32_t n, int H, float* out, cudaStream_t s);
 int launch_lse_finish(const float2* partials, const float* label_logit, int32_t n_copies, int n_tiles,
                       float* tok_logp, cudaStream_t s);
 int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,

@@ -285,6 +285,155 @@ __global__ void attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfl
   }
 }
 
+// ---------------------------------------------------------------- tensor-core varlen attention
+// One warp per (masked copy, head), flash-style: 16-query tiles x 16-key blocks with an
+// online softmax, S = Q K^T and O = P V on mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
+// Per-sequence tiles are 5..66 rows, far below the 128-row tcgen05 atom, and the two
+// matmuls are 0.4 % of the path's FLOPs: the warp-level MMA keeps every
+// tile busy with no padding to 128 and leaves the kernel HBM-bound (6 KB per token).
+// Q / K fragments are read straight from global memory (each element is used once per
+// tile); V blocks are staged in shared memory and read with ldmatrix.trans.
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_VROW = 72;   // bf16 elements per staged V row (144 B: conflict-free ldmatrix)
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
+                     int32_t n_copies, int H, int NH) {
+  __shared__ __align__(16) __nv_bfloat16 vs_all[ATT_WARPS][16 * ATT_VROW];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * ATT_WARPS + wib;
+  if (pair >= (int64_t)n_copies * NH) return;
+  const int c = (int)(pair / NH), head = (int)(pair % NH);
+  const int start = plan.seq_start[c], T = plan.seq_len[c];
+  const int g = lane >> 2, cq = lane & 3;
+  const size_t ld = (size_t)3 * H;
+  const __nv_bfloat16* qb = qkv + (size_t)start * ld + head * 64;
+  const __nv_bfloat16* kb = qb + H;
+  const __nv_bfloat16* vb = qb + 2 * H;
+  __nv_bfloat16* vs = vs_all[wib];
+  const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(vs);
+  constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // head_dim**-0.5 * log2(e)
+
+  for (int m0 = 0; m0 < T; m0 += 16) {
+    const int r0 = min(m0 + g, T - 1), r1 = min(m0 + g + 8, T - 1);
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qf[ks][0] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ld + 16 * ks + 2 * cq);
+      qf[ks][1] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ld + 16 * ks + 2 * cq);
+      qf[ks][2] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ld + 16 * ks + 8 + 2 * cq);
+      qf[ks][3] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ld + 16 * ks + 8 + 2 * cq);
+    }
+    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+
+    for (int k0 = 0; k0 < T; k0 += 16) {
+      // stage V[k0 .. k0+15][0..63] (rows clamped to T-1: masked keys get p = 0, values stay finite)
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = i * 4 + (lane >> 3), ch = lane & 7;
+        const int key = min(k0 + row, T - 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(vb + (size_t)key * ld + ch * 8);
+        *reinterpret_cast<uint4*>(vs + row * ATT_VROW + ch * 8) = v;
+      }
+      // S block = Q K^T for keys k0..k0+15 (two n-tiles of 8 keys)
+      float s[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const int key = min(k0 + 8 * j + g, T - 1);
+        const __nv_bfloat16* kr = kb + (size_t)key * ld + 2 * cq;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + 16 * ks);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 16 * ks + 8);
+          mma_bf16_16816(s[j], qf[ks], b0, b1);
+        }
+      }
+      // mask keys >= T, scale into the log2 domain, online softmax (rows g and g+8)
+      float bm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = k0 + 8 * j + 2 * cq + (e & 1);
+          s[j][e] = key < T ? s[j][e] * kScaleLog2 : -INFINITY;
+          bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
+        }
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
+        const float nm = fmaxf(mx[r], bm[r]);       // finite: every key block holds >= 1 valid key
+        corr[r] = exp2f(mx[r] - nm);
+        mx[r] = nm;
+        l[r] *= corr[r];
+      }
+      uint32_t pf[4];
+      {
+        const float p00 = exp2f(s[0][0] - mx[0]), p01 = exp2f(s[0][1] - mx[0]);
+        const float p02 = exp2f(s[0][2] - mx[1]), p03 = exp2f(s[0][3] - mx[1]);
+        const float p10 = exp2f(s[1][0] - mx[0]), p11 = exp2f(s[1][1] - mx[0]);
+        const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
+        l[0] += (p00 + p01) + (p10 + p11);
+        l[1] += (p02 + p03) + (p12 + p13);
+        pf[0] = pack2_bf16(p00, p01); pf[1] = pack2_bf16(p02, p03);
+        pf[2] = pack2_bf16(p10, p11); pf[3] = pack2_bf16(p12, p13);
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1];
+      }
+      __syncwarp();   // V block visible to the whole warp
+      // O += P V : 8 d-tiles of 8 columns, V^T fragments via ldmatrix.trans
+#pragma unroll
+      for (int n = 0; n < 8; n += 2) {
+        const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8;      // key row inside the block
+        const int mcol = 8 * n + ((lane >> 4) & 1) * 8;           // d column of the 8x8 matrix
+        const uint32_t addr = vs_addr + (uint32_t)(mrow * ATT_VROW + mcol) * 2;
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+        mma_bf16_16816(o[n], pf, b0, b1);
+        mma_bf16_16816(o[n + 1], pf, b2, b3);
+      }
+    }
+    // finish: row sums across the quad, normalise, store bf16
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+    const int q0 = m0 + g, q1 = m0 + g + 8;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (q0 < T)
+        *reinterpret_cast<uint32_t*>(ctx + (size_t)(start + q0) * H + head * 64 + 8 * n + 2 * cq) =
+            pack2_bf16(o[n][0] * inv0, o[n][1] * inv0);
+      if (q1 < T)
+        *reinterpret_cast<uint32_t*>(ctx + (size_t)(start + q1) * H + head * 64 + 8 * n + 2 * cq) =
+            pack2_bf16(o[n][2] * inv1, o[n][3] * inv1);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- head helpers
 __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows,
                                         int32_t n, int H, __nv_bfloat16* __restrict__ dst) {
@@ -294,6 +443,16 @@ __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, c
   const uint4* s = reinterpret_cast<const uint4*>(src + (size_t)rows[c] * H);
   uint4* d = reinterpret_cast<uint4*>(dst + (size_t)c * H);
   for (int i = lane; i < H / 8; i += 32) d[i] = s[i];
+}
+
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, int32_t n, int H,
+                                       float* __restrict__ dst) {
+  const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n) return;
+  const float4* s = reinterpret_cast<const float4*>(src + (size_t)rows[c] * H);
+  float4* d = reinterpret_cast<float4*>(dst + (size_t)c * H);
+  for (int i = lane; i < H / 4; i += 32) d[i] = s[i];
 }
 
 // log_softmax(logits)[label] = label_logit - (max + log(sum exp)) — MLM_PLL/main.py:101-105
@@ -412,6 +571,20 @@ int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_
                      cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
+  (void)max_T;
+  const int64_t pairs = (int64_t)n_copies * NH;
+  attention_mma_kernel<<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, 0, s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
+      NH);
+  PLLB_LAUNCH_CHECK("attention_mma_kernel");
+  return PLLB_OK;
+}
+
+// fp32 SIMT attention (validation kernel: tests compare the tensor-core kernel against it)
+int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
+                          int max_T, cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
   const int Tp = max_T | 1;
   size_t per_warp = (size_t)64 * Tp * 2 + (size_t)Tp * 64 * 2 + 64 * ATT_QB * 4 + 32 * ATT_QB * 4;
   per_warp = (per_warp + 15) & ~(size_t)15;
@@ -433,6 +606,13 @@ int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_
   gather_rows_bf16_kernel<<<(unsigned)ceil_div(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(hidden_bf16), rows, n, H, reinterpret_cast<__nv_bfloat16*>(out));
   PLLB_LAUNCH_CHECK("gather_rows_bf16_kernel");
+  return PLLB_OK;
+}
+
+int launch_gather_rows_f32(const float* src, const int32_t* rows, int32_t n, int H, float* out, cudaStream_t s) {
+  if (n <= 0) return PLLB_OK;
+  gather_rows_f32_kernel<<<(unsigned)ceil_div(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(src, rows, n, H, out);
+  PLLB_LAUNCH_CHECK("gather_rows_f32_kernel");
   return PLLB_OK;
 }
 

@@ -14,7 +14,8 @@
 //              stage; accumulators live in TMEM (2 x 256 fp32 columns, double buffered so
 //              the epilogue of tile i overlaps the MMAs of tile i+1); tcgen05.commit frees
 //              smem stages and publishes finished accumulators.
-//   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns per warp), bias / erf-GELU /
+//   warps 2-9: epilogue (two warps per TMEM lane quarter, half of the tile's columns each)
+//              — tcgen05.ld (32 lanes x 32 columns per warp), bias / erf-GELU /
 //              dtype conversion in registers, 128-byte-swizzled staging in shared memory
 //              and TMA stores; or, for the decoder, an online logsumexp over the vocab
 //              tile plus the label-column pick, so the [copies x V] logits never exist.
@@ -36,9 +37,10 @@ constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;                 // two per TMEM lane quarter, each owning half of the BN columns
+constexpr int EPI_COLS = BN / 2;             // columns per epilogue warp
 constexpr int EPI_BUF_BYTES = 32 * 128;      // one 32-row x 128-byte swizzled box
-constexpr int EPI_BUFS = 2;                  // per epilogue warp
+constexpr int EPI_BUFS = 1;                  // per epilogue warp
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;               // 2 accumulator stages x BN columns
 constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
@@ -52,9 +54,20 @@ struct KParams {
   LseArgs lse;
 };
 
+// HF activations "gelu" = nn.functional.gelu (erf form): 0.5 x (1 + erf(x / sqrt 2)).
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): two MUFU ops + 7 FMAs instead of
+// erff's ~30 instructions — the epilogue, not the MMA, paces the FFN1 GEMM otherwise.
+// 1 + erf(x) is formed without cancellation on the negative side.
 __device__ __forceinline__ float gelu_erf(float x) {
-  // HF activations "gelu" = nn.functional.gelu (erf form)
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float pe = p * t * __expf(-z * z);          // 1 - erf(|x| / sqrt 2)
+  const float one_plus_erf = x >= 0.f ? 2.0f - pe : pe;
+  return 0.5f * x * one_plus_erf;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -160,9 +173,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                               // TMEM lane quarter this warp may read
     const int ew = warp - 2;
+    const int cbase = (ew >> 2) * EPI_COLS;               // first tile column owned by this warp
     const uint32_t my_buf = sEpi + ew * EPI_BUFS * EPI_BUF_BYTES;
     uint32_t acc = 0, acc_phase = 0;
-    uint32_t buf_i = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BM;
       const int tn = tile % tiles_n;
@@ -176,7 +189,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int label = (row < p.M) ? p.lse.labels[row] : -1;
         float run_max = -INFINITY, run_sum = 0.f, lab_val = 0.f;
         bool has_label = false;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cbase; c0 < cbase + EPI_COLS; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_addr + c0, r);
           tcgen05_wait_ld();
@@ -201,17 +214,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (row < p.M) {
-          p.lse.partials[(size_t)row * tiles_n + tn] = make_float2(run_max, run_sum);
+          p.lse.partials[((size_t)row * tiles_n + tn) * 2 + (ew >> 2)] = make_float2(run_max, run_sum);
           if (has_label) p.lse.label_logit[row] = lab_val;
         }
       } else if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
-        for (int c0 = 0; c0 < BN; c0 += 64) {
+        for (int c0 = cbase; c0 < cbase + EPI_COLS; c0 += 64) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(t_addr + c0, r0);
           tmem_ld_32x32b_x32(t_addr + c0 + 32, r1);
           tcgen05_wait_ld();
-          const uint32_t buf = my_buf + (buf_i & 1) * EPI_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<1>();         // the store that last read this buffer is done
+          const uint32_t buf = my_buf;
+          if (lane == 0) tma_store_wait_read<0>();         // the store that last read this buffer is done
           __syncwarp();
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
@@ -240,15 +253,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_2d(&tmC, buf, n0 + c0, m0 + q * 32);
             tma_store_commit();
           }
-          ++buf_i;
         }
       } else {  // fp32 output
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cbase; c0 < cbase + EPI_COLS; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_addr + c0, r);
           tcgen05_wait_ld();
-          const uint32_t buf = my_buf + (buf_i & 1) * EPI_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<1>();
+          const uint32_t buf = my_buf;
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
@@ -272,7 +284,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_2d(&tmC, buf, n0 + c0, m0 + q * 32);
             tma_store_commit();
           }
-          ++buf_i;
         }
       }
       // all tcgen05.ld of this accumulator have completed (wait::ld above): release it

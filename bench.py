@@ -309,8 +309,9 @@ def main():
 
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
-        gf = gemm_flops(lens, cfg)
-        achieved = gf / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        gf = gemm_flops(lens, cfg)                      # SURVEY.md §8(d) formula (all T rows in every layer)
+        gf_exec = st["gemm_flops"] / args.steps         # 2*M*N*K summed over the launches of one step
+        achieved = gf_exec / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
@@ -334,7 +335,8 @@ def main():
                          "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "launches_per_step": int(gemm_launches),
                          "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_value,
-                         "algorithmic_gemm_tflop_per_step": gf / 1e12,
+                         "executed_gemm_tflop_per_step": gf_exec / 1e12,
+                         "survey_formula_gemm_tflop_per_step": gf / 1e12,
                          "ms_by_kind": st["gemm_ms_by_kind"]},
             "whole_step_tflops": total_flops(lens, cfg) / (ms_value / 1e3) / 1e12,
             "pll_checksum": float(np.sum(pll_host)), "best_weight": float(weights[int(np.argmin(es_host))]),
