@@ -126,6 +126,33 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+// ---------------------------------------------------------------- packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2)
+// Two fp32 lanes per instruction: halves the FMA-pipe issue slots of the GEMM epilogues.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2,%3};\n\t mov.b64 rb, {%4,%5};\n\t mov.b64 rc, {%6,%7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2,%3};\n\t mov.b64 rb, {%4,%5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2,%3};\n\t mov.b64 rb, {%4,%5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // K-major operand tile in the 128-byte-swizzle canonical layout (what a TMA box of
 // 64 bf16 x R rows with CU_TENSOR_MAP_SWIZZLE_128B produces): 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
