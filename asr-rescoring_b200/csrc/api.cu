@@ -318,6 +318,33 @@ int check_device() {
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Grow-only device scratch for the stage-4 host entry points (one per host thread and
+// device): repeated sweeps must not pay cudaMalloc / cudaFree (an implicit device sync).
+struct Scratch {
+  void* p = nullptr;
+  int64_t cap = 0;
+  int dev = -1;
+};
+thread_local Scratch g_scratch;
+
+int get_scratch(int64_t bytes, uint8_t** out) {
+  int dev = 0;
+  PLLB_CUDA(cudaGetDevice(&dev));
+  if (g_scratch.dev != dev || g_scratch.cap < bytes) {
+    if (g_scratch.p) {
+      PLLB_CUDA(cudaDeviceSynchronize());
+      cudaFree(g_scratch.p);
+      g_scratch = Scratch{};
+    }
+    const int64_t cap = bytes + bytes / 2 + (1 << 20);
+    PLLB_CUDA(cudaMalloc(&g_scratch.p, (size_t)cap));
+    g_scratch.cap = cap;
+    g_scratch.dev = dev;
+  }
+  *out = reinterpret_cast<uint8_t*>(g_scratch.p);
+  return PLLB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -618,7 +645,7 @@ int pllb_levenshtein_host(const int32_t* ref_cp, const int64_t* ref_off, int32_t
                 b2 = align_up(4 * std::max<int64_t>(n_hc, 1), 256), b3 = align_up(8 * (int64_t)(n_pairs + 1), 256),
                 b4 = align_up(4 * (int64_t)n_pairs, 256), b5 = b4;
   uint8_t* base = nullptr;
-  PLLB_CUDA(cudaMalloc(&base, (size_t)(b0 + b1 + b2 + b3 + b4 + b5)));
+  RC(get_scratch(b0 + b1 + b2 + b3 + b4 + b5, &base));
   int32_t* d_rc = (int32_t*)base;
   int64_t* d_ro = (int64_t*)(base + b0);
   int32_t* d_hc = (int32_t*)(base + b0 + b1);
@@ -636,7 +663,6 @@ int pllb_levenshtein_host(const int32_t* ref_cp, const int64_t* ref_off, int32_t
   if (e == cudaSuccess) rc = launch_levenshtein(d_rc, d_ro, d_hc, d_ho, d_pr, n_pairs, max_len, d_out, s);
   if (e == cudaSuccess && rc == PLLB_OK) e = cudaMemcpyAsync(out_dist, d_out, 4 * (int64_t)n_pairs, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess && rc == PLLB_OK) e = cudaStreamSynchronize(s);
-  cudaFree(base);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("pllb_levenshtein_host: ") + cudaGetErrorString(e));
   return PLLB_OK;
@@ -660,7 +686,7 @@ int pllb_rescore_sweep_host(const double* am, const double* lm, const int64_t* l
   const int64_t b_d = align_up(8 * n, 256), b_i = align_up(4 * n, 256), b_w = align_up(8 * (int64_t)W, 256),
                 b_a = align_up(4 * (int64_t)W * N, 256);
   uint8_t* base = nullptr;
-  PLLB_CUDA(cudaMalloc(&base, (size_t)(3 * b_d + b_i + 2 * b_w + b_a)));
+  RC(get_scratch(3 * b_d + b_i + 2 * b_w + b_a, &base));
   double* d_am = (double*)base;
   double* d_lm = (double*)(base + b_d);
   int64_t* d_len = (int64_t*)(base + 2 * b_d);
@@ -682,7 +708,6 @@ int pllb_rescore_sweep_host(const double* am, const double* lm, const int64_t* l
   if (e == cudaSuccess && rc == PLLB_OK && out_edit_sum)
     e = cudaMemcpyAsync(out_edit_sum, d_es, 8 * (int64_t)W, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess && rc == PLLB_OK) e = cudaStreamSynchronize(s);
-  cudaFree(base);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("pllb_rescore_sweep_host: ") + cudaGetErrorString(e));
   return PLLB_OK;

@@ -243,11 +243,18 @@ def main():
     h_tok, h_am, h_len = pin(tok), pin(am), pin(hyp_len)
     h_pll = torch.zeros(n_hyp, dtype=torch.float64).pin_memory().numpy()
 
+    e2e_parts = [0.0, 0.0, 0.0]
+
     def step_host():
+        t0 = time.perf_counter()
         pll = scorer.score_packed(h_tok, off)
+        t1 = time.perf_counter()
         h_pll[:] = pll
         dist_h = engine.levenshtein_packed(rc, ro, hc, ho, pair_ref).reshape(N, n_best)
+        t2 = time.perf_counter()
         arg, es = engine.rescore_sweep(h_am, h_pll.reshape(N, n_best), h_len, dist_h, weights, "B")
+        t3 = time.perf_counter()
+        e2e_parts[0] += t1 - t0; e2e_parts[1] += t2 - t1; e2e_parts[2] += t3 - t2
         return pll, es
 
     h2d = tok.nbytes + (rc.nbytes + ro.nbytes + hc.nbytes + ho.nbytes + pair_ref.nbytes) + \
@@ -287,6 +294,7 @@ def main():
     for _ in range(min(args.warmup, 1)):
         step_host()
     barrier()
+    e2e_parts[:] = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         pll_host, es_host = step_host()
@@ -328,7 +336,10 @@ def main():
                        "l2": "activations per chunk (>= 15 GB) exceed L2; no flush needed",
                        "algorithmic_tflop_per_step_per_gpu": total_flops(lens, cfg) / 1e12},
             "e2e": {"value": total_hyps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                    "ms_parts": {"pllb_score_host": 1e3 * e2e_parts[0] / args.steps,
+                                 "pllb_levenshtein_host": 1e3 * e2e_parts[1] / args.steps,
+                                 "pllb_rescore_sweep_host": 1e3 * e2e_parts[2] / args.steps}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak_tf,
