@@ -307,21 +307,11 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(ATT_WARPS * 32)
-attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
-                     int32_t n_copies, int H, int NH) {
-  __shared__ __align__(16) __nv_bfloat16 vs_all[ATT_WARPS][16 * ATT_VROW];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t pair = (int64_t)blockIdx.x * ATT_WARPS + wib;
-  if (pair >= (int64_t)n_copies * NH) return;
-  const int c = (int)(pair / NH), head = (int)(pair % NH);
-  const int start = plan.seq_start[c], T = plan.seq_len[c];
+// Streaming form: any T; V blocks staged per 16-key block, Q/K fragments straight from global.
+__device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb, const __nv_bfloat16* __restrict__ kb,
+                                            const __nv_bfloat16* __restrict__ vb, __nv_bfloat16* __restrict__ ob,
+                                            int T, size_t ld, int H, int lane, __nv_bfloat16* vs) {
   const int g = lane >> 2, cq = lane & 3;
-  const size_t ld = (size_t)3 * H;
-  const __nv_bfloat16* qb = qkv + (size_t)start * ld + head * 64;
-  const __nv_bfloat16* kb = qb + H;
-  const __nv_bfloat16* vb = qb + 2 * H;
-  __nv_bfloat16* vs = vs_all[wib];
   const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(vs);
   constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // head_dim**-0.5 * log2(e)
 
@@ -425,13 +415,144 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       if (q0 < T)
-        *reinterpret_cast<uint32_t*>(ctx + (size_t)(start + q0) * H + head * 64 + 8 * n + 2 * cq) =
-            pack2_bf16(o[n][0] * inv0, o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][0] * inv0, o[n][1] * inv0);
       if (q1 < T)
-        *reinterpret_cast<uint32_t*>(ctx + (size_t)(start + q1) * H + head * 64 + 8 * n + 2 * cq) =
-            pack2_bf16(o[n][2] * inv1, o[n][3] * inv1);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][2] * inv1, o[n][3] * inv1);
     }
   }
+}
+
+// Staged form for T <= ATT_TS: the whole Q, K, V head slices of the sequence are brought
+// into shared memory with one burst of cp.async (a single memory latency per sequence
+// instead of one per 16x16 block), then every fragment comes from ldmatrix.
+constexpr int ATT_TS = 32;
+constexpr int ATT_STAGE_ELEMS = 3 * ATT_TS * ATT_VROW;   // bf16 elements per warp (13.5 KiB)
+
+__device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb, __nv_bfloat16* __restrict__ ob, int T,
+                                            size_t ld, int H, int lane, __nv_bfloat16* sm) {
+  const int g = lane >> 2, cq = lane & 3;
+  const uint32_t sm_addr = (uint32_t)__cvta_generic_to_shared(sm);
+  constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
+  __syncwarp();                                           // previous sequence's fragments consumed
+  for (int i = lane; i < 24 * T; i += 32) {               // 3 matrices x T rows x 8 chunks of 16 B
+    const int mat = i / (8 * T), rem = i - mat * 8 * T, r = rem >> 3, ch = rem & 7;
+    const __nv_bfloat16* src = qb + (size_t)r * ld + (size_t)mat * H + ch * 8;
+    const uint32_t dst = sm_addr + (uint32_t)((mat * ATT_TS + r) * ATT_VROW + ch * 8) * 2;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+  const uint32_t q_addr = sm_addr, k_addr = sm_addr + ATT_TS * ATT_VROW * 2, v_addr = sm_addr + 2 * ATT_TS * ATT_VROW * 2;
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol8 = ((lane >> 4) & 1) * 8;
+
+  for (int m0 = 0; m0 < T; m0 += 16) {
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t addr = q_addr + (uint32_t)((m0 + lrow) * ATT_VROW + 16 * ks + lcol8) * 2;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(qf[ks][0]), "=r"(qf[ks][1]), "=r"(qf[ks][2]), "=r"(qf[ks][3]) : "r"(addr));
+    }
+    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    for (int k0 = 0; k0 < T; k0 += 16) {
+      float s[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {                 // two k-steps per ldmatrix.x4
+          const uint32_t addr = k_addr + (uint32_t)((k0 + 8 * j + (lane & 7)) * ATT_VROW + 32 * kp + (lane >> 3) * 8) * 2;
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+          mma_bf16_16816(s[j], qf[2 * kp], b0, b1);
+          mma_bf16_16816(s[j], qf[2 * kp + 1], b2, b3);
+        }
+      }
+      float bm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = k0 + 8 * j + 2 * cq + (e & 1);
+          s[j][e] = key < T ? s[j][e] * kScaleLog2 : -INFINITY;
+          bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
+        }
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
+        const float nm = fmaxf(mx[r], bm[r]);
+        corr[r] = exp2f(mx[r] - nm);
+        mx[r] = nm;
+        l[r] *= corr[r];
+      }
+      uint32_t pf[4];
+      {
+        const float p00 = exp2f(s[0][0] - mx[0]), p01 = exp2f(s[0][1] - mx[0]);
+        const float p02 = exp2f(s[0][2] - mx[1]), p03 = exp2f(s[0][3] - mx[1]);
+        const float p10 = exp2f(s[1][0] - mx[0]), p11 = exp2f(s[1][1] - mx[0]);
+        const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
+        l[0] += (p00 + p01) + (p10 + p11);
+        l[1] += (p02 + p03) + (p12 + p13);
+        pf[0] = pack2_bf16(p00, p01); pf[1] = pack2_bf16(p02, p03);
+        pf[2] = pack2_bf16(p10, p11); pf[3] = pack2_bf16(p12, p13);
+      }
+      if (k0 > 0) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1];
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 8; n += 2) {
+        const uint32_t addr = v_addr + (uint32_t)((k0 + lrow) * ATT_VROW + 8 * n + lcol8) * 2;
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+        mma_bf16_16816(o[n], pf, b0, b1);
+        mma_bf16_16816(o[n + 1], pf, b2, b3);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+    const int q0 = m0 + g, q1 = m0 + g + 8;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (q0 < T)
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][0] * inv0, o[n][1] * inv0);
+      if (q1 < T)
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][2] * inv1, o[n][3] * inv1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32, 2)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
+                     int32_t n_copies, int H, int NH) {
+  extern __shared__ __align__(16) uint8_t att_dyn[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_dyn) + (size_t)wib * ATT_STAGE_ELEMS;
+  // rows T..31 of the staging area are read as masked keys / unused queries: keep them finite
+  for (int i = lane; i < ATT_STAGE_ELEMS / 8; i += 32) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  const int64_t pair = (int64_t)blockIdx.x * ATT_WARPS + wib;
+  if (pair >= (int64_t)n_copies * NH) return;
+  const int c = (int)(pair / NH), head = (int)(pair % NH);
+  const int start = plan.seq_start[c], T = plan.seq_len[c];
+  const size_t ld = (size_t)3 * H;
+  const __nv_bfloat16* qb = qkv + (size_t)start * ld + head * 64;
+  __nv_bfloat16* ob = ctx + (size_t)start * H + head * 64;
+  if (T <= ATT_TS) attn_staged(qb, ob, T, ld, H, lane, sm);
+  else attn_stream(qb, qb + H, qb + 2 * H, ob, T, ld, H, lane, sm);
 }
 
 // ---------------------------------------------------------------- head helpers
@@ -573,7 +694,9 @@ int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_
   if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
   (void)max_T;
   const int64_t pairs = (int64_t)n_copies * NH;
-  attention_mma_kernel<<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, 0, s>>>(
+  const int smem = ATT_WARPS * ATT_STAGE_ELEMS * 2;
+  PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  attention_mma_kernel<<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
       NH);
   PLLB_LAUNCH_CHECK("attention_mma_kernel");

@@ -186,6 +186,23 @@ def test_embeddings_and_layers_vs_oracle():
             assert err.max().item() < 0.03 and err.mean().item() < 3e-3   # bf16 GEMM operands
 
 
+def test_attention_paths_short_and_long_sequences():
+    """T <= 32 takes the cp.async-staged attention path, longer sequences the streaming one;
+    both against the fp32 oracle after one full layer, incl. T = 3 and T = max_position."""
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 12, perturb=True)
+    rng = np.random.default_rng(3)
+    lens = [1, 2, 14, 15, 16, 29, 30, 31, 32, 47, 64, 100, cfg["max_position"] - 2]
+    off = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rng.integers(104, cfg["vocab"], size=int(off[-1])).astype(np.int32)
+    with engine.PllScorer(sd, cfg) as sc:
+        got = sc.hidden(tok, off, 1)
+    exp = _oracle_hidden(sd, cfg, tok, off, 1)
+    err = (got - exp).abs()
+    assert err.max().item() < 0.03 and err.mean().item() < 3e-3, (err.max().item(), err.mean().item())
+
+
 def test_pll_vs_reference_golden(gold_dir):
     gold = json.load(open(os.path.join(gold_dir, "pll_golden.json")))
     for case in gold["cases"]:
