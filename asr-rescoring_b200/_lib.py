@@ -20,7 +20,7 @@ class PllbError(RuntimeError):
 class ModelDesc(ctypes.Structure):
     _fields_ = [("num_layers", c_int32), ("hidden", c_int32), ("num_heads", c_int32), ("intermediate", c_int32),
                 ("vocab", c_int32), ("max_position", c_int32), ("ln_eps", c_float),
-                ("cls_id", c_int32), ("sep_id", c_int32), ("mask_id", c_int32)]
+                ("cls_id", c_int32), ("sep_id", c_int32), ("mask_id", c_int32), ("operand_dtype", c_int32)]
 
 
 _LAYER_FIELDS = ["q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "ao_w", "ao_b", "ao_ln_g", "ao_ln_b",

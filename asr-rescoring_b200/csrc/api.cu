@@ -53,6 +53,7 @@ struct TimedLaunch {
 struct pllb_context {
   pllb_model_desc d{};
   int device = 0;
+  bool fp16 = false;                 // GEMM operand dtype: bf16 (default) or IEEE fp16
   int64_t cap_rows = 0, cap_copies = 0, cap_hyps = 0;
   int vocab_pad = 0, tiles_v = 0;
   std::vector<void*> owned;          // every cudaMalloc of this handle
@@ -114,7 +115,7 @@ int copy_f32(pllb_context* c, float** dst, const float* src, int64_t n, cudaStre
 int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n, cudaStream_t s) {
   int rc = dev_alloc(c, dst, n);
   if (rc) return rc;
-  return launch_f32_to_bf16(src, *dst, n, s);
+  return launch_f32_to_bf16(src, *dst, n, c->fp16, s);
 }
 
 #define RC(expr)            \
@@ -137,7 +138,7 @@ int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const fl
     tl->kind = kind;
     PLLB_CUDA(cudaEventRecord(tl->start, s));
   }
-  RC(launch_gemm_tcgen05(A, W, bias, C, M, N, K, epi, lse, s));
+  RC(launch_gemm_tcgen05(A, W, bias, C, M, N, K, epi, lse, c->fp16, s));
   if (tl) PLLB_CUDA(cudaEventRecord(tl->stop, s));
   const double fl = 2.0 * (double)M * (double)(epi == EPI_LSE && lse ? lse->vocab : N) * (double)K;
   c->stats.gemm_flops += fl;
@@ -155,7 +156,7 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   const int H = d.hidden, I = d.intermediate;
   RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, c->plan, s));
   RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
-                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->hidden_f32, c->hidden_bf16, s));
+                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->hidden_f32, c->hidden_bf16, c->fp16, s));
   const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
   // Only the [MASK] row of each copy reaches the MLM head (MLM_PLL/main.py:101), and after the
   // last layer's attention every remaining op is row-wise: the last layer's output
@@ -165,29 +166,29 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   for (int l = 0; l < n_layers; ++l) {
     const LayerDev& L = c->layers[l];
     RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide, n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
-    RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, s));
+    RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, s));
     if (prune_last && l == n_layers - 1) {
       RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
       RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
       RC(timed_gemm(c, G_AO, c->hg, L.ao_w, L.ao_b, c->y_f32, n_copies, H, H, EPI_BIAS_F32, nullptr, s));
-      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.ao_g, L.ao_be, d.ln_eps, n_copies, H, s));
+      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.ao_g, L.ao_be, d.ln_eps, n_copies, H, c->fp16, s));
       RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
       RC(timed_gemm(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, c->y_f32, n_copies, H, I, EPI_BIAS_F32, nullptr, s));
-      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.out_g, L.out_be, d.ln_eps, n_copies, H, s));
+      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.out_g, L.out_be, d.ln_eps, n_copies, H, c->fp16, s));
       break;
     }
     RC(timed_gemm(c, G_AO, c->ctx, L.ao_w, L.ao_b, c->y_f32, n_rows, H, H, EPI_BIAS_F32, nullptr, s));
-    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.ao_g, L.ao_be, d.ln_eps, n_rows, H, s));
+    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.ao_g, L.ao_be, d.ln_eps, n_rows, H, c->fp16, s));
     RC(timed_gemm(c, G_FF1, c->hidden_bf16, L.ff1_w, L.ff1_b, c->wide, n_rows, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
     RC(timed_gemm(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, c->y_f32, n_rows, H, I, EPI_BIAS_F32, nullptr, s));
-    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.out_g, L.out_be, d.ln_eps, n_rows, H, s));
+    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.out_g, L.out_be, d.ln_eps, n_rows, H, c->fp16, s));
   }
   if (upto_layer >= 0) return PLLB_OK;
   // MLM head at the masked row of every copy only (the reference evaluates all B*T rows,
   // transformers modeling_bert.py:975, and keeps one: MLM_PLL/main.py:101).
   if (!prune_last) RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->t_bf16, s));
   RC(timed_gemm(c, G_HEAD, c->t_bf16, c->head_w, c->head_b, c->t_f32, n_copies, H, H, EPI_BIAS_GELU_F32, nullptr, s));
-  RC(launch_plain_ln_bf16(c->t_f32, c->hg, c->head_g, c->head_be, d.ln_eps, n_copies, H, s));
+  RC(launch_plain_ln_bf16(c->t_f32, c->hg, c->head_g, c->head_be, d.ln_eps, n_copies, H, c->fp16, s));
   LseArgs lse{c->plan.label, c->partials, c->label_logit, d.vocab};
   RC(timed_gemm(c, G_DEC, c->hg, c->dec_w, c->dec_b, nullptr, n_copies, c->vocab_pad, H, EPI_LSE, &lse, s));
   RC(launch_lse_finish(c->partials, c->label_logit, n_copies, 2 * c->tiles_v, c->tok_logp, s));
@@ -373,7 +374,8 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   RC(check_device());
   const pllb_model_desc& d = *desc;
   if (d.hidden % 256 != 0 || d.hidden < 256 || d.hidden > 1024 || d.num_heads * 64 != d.hidden ||
-      d.intermediate % 256 != 0 || d.num_layers < 0 || d.vocab < 1 || d.max_position < 3)
+      d.intermediate % 256 != 0 || d.num_layers < 0 || d.vocab < 1 || d.max_position < 3 ||
+      (d.operand_dtype != 0 && d.operand_dtype != 1))
     return fail(PLLB_ERR_INVALID, "unsupported model shape: need hidden in {256,512,768,1024}, head dim 64, "
                                   "intermediate % 256 == 0");
   PLLB_CUDA(cudaSetDevice(device));
@@ -383,6 +385,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   pllb_context* c = new pllb_context();
   c->d = d;
   c->device = device;
+  c->fp16 = d.operand_dtype == 1;
   cudaStream_t s = 0;
   const int H = d.hidden, I = d.intermediate, V = d.vocab;
   int rc = PLLB_OK;
@@ -405,9 +408,9 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
     const pllb_layer_weights& lw = w->layers[l];
     LayerDev& L = c->layers[l];
     TRY(dev_alloc(c, &L.qkv_w, (int64_t)3 * H * H));
-    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, s));
-    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, s));
-    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, s));
+    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->fp16, s));
     TRY(dev_alloc(c, &L.qkv_b, 3 * H));
     cudaMemcpyAsync(L.qkv_b, lw.q_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(L.qkv_b + H, lw.k_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
@@ -431,7 +434,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   c->tiles_v = c->vocab_pad / 256;
   TRY(dev_alloc(c, &c->dec_w, (int64_t)c->vocab_pad * H));
   cudaMemsetAsync(c->dec_w, 0, sizeof(__nv_bfloat16) * (size_t)c->vocab_pad * H, s);
-  TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, s));
+  TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->fp16, s));
   TRY(dev_alloc(c, &c->dec_b, c->vocab_pad));
   cudaMemsetAsync(c->dec_b, 0, sizeof(float) * c->vocab_pad, s);
   cudaMemcpyAsync(c->dec_b, w->decoder_b, sizeof(float) * V, cudaMemcpyDeviceToDevice, s);
@@ -604,7 +607,7 @@ int pllb_debug_gemm(const uint16_t* A, const uint16_t* W, const float* bias, voi
                     int32_t epilogue, void* stream) {
   RC(check_device());
   if (epilogue < 0 || epilogue > 3) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm: epilogue must be 0..3");
-  return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, (cudaStream_t)stream);
+  return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, false, (cudaStream_t)stream);
 }
 
 int pllb_debug_gemm_simt(const uint16_t* A, const uint16_t* W, const float* bias, void* C, int32_t M, int32_t N,

@@ -53,8 +53,9 @@ struct LseArgs {
 
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A, W bf16 row-major (K contiguous).
 // N % 256 == 0 (pad W rows with zeros), K % 64 == 0.  ldc = N.
+// fp16 = operands (and 16-bit outputs) are IEEE half instead of bf16.
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                        int epilogue, const LseArgs* lse, cudaStream_t stream);
+                        int epilogue, const LseArgs* lse, bool fp16, cudaStream_t stream);
 int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                      int epilogue, cudaStream_t stream);
 
@@ -75,15 +76,15 @@ int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPla
 int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                     const float* word_emb, const float* pos_emb, const float* type_emb, const float* g,
                     const float* b, float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id,
-                    float* hidden_f32, void* hidden_bf16, cudaStream_t s);
+                    float* hidden_f32, void* hidden_bf16, bool fp16, cudaStream_t s);
 // hidden = LN(y + hidden) (in place), hidden_bf16 = bf16(hidden)
 int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b,
-                       float eps, int64_t rows, int H, cudaStream_t s);
+                       float eps, int64_t rows, int H, bool fp16, cudaStream_t s);
 // out_bf16 = bf16(LN(x)); no residual (MLM head transform)
 int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const float* b, float eps, int64_t rows,
-                         int H, cudaStream_t s);
+                         int H, bool fp16, cudaStream_t s);
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
-                     int max_T, cudaStream_t s);
+                     int max_T, bool fp16, cudaStream_t s);
 int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
                           int max_T, cudaStream_t s);
 int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out,
@@ -93,7 +94,7 @@ int launch_lse_finish(const float2* partials, const float* label_logit, int32_t 
                       float* tok_logp, cudaStream_t s);
 int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,
                    float* out_tok_logp, cudaStream_t s);
-int launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s);
+int launch_f32_to_bf16(const float* src, void* dst, int64_t n, bool fp16, cudaStream_t s);
 
 // ---- combiner (rescore_kernels.cu, compiled with -fmad=false) ------------------
 int launch_rescore_sweep(const double* am, const double* lm, const int64_t* len, const int32_t* dist, int32_t N,

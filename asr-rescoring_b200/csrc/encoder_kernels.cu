@@ -8,6 +8,7 @@
 // All kernels are one-warp-per-row (or per sequence/head) with 128-bit accesses; rows of
 // H fp32 are contiguous so every warp access is a fully coalesced 512-byte segment.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.h"
 
@@ -26,6 +27,19 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// two fp32 -> packed 16-bit pair in the operand dtype (bf16 or fp16); buffers are typed
+// __nv_bfloat16 throughout and reinterpreted when the handle runs in fp16 mode.
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  if constexpr (FP16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
 }
 
 // ---------------------------------------------------------------- plan
@@ -106,17 +120,16 @@ __device__ __forceinline__ void ln_normalize(float4 (&x)[VEC], const float* __re
   }
 }
 
-template <int VEC>
+template <int VEC, bool FP16>
 __device__ __forceinline__ void store_row(const float4 (&x)[VEC], float* __restrict__ f32_row,
                                           __nv_bfloat16* __restrict__ bf_row, int lane) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     if (f32_row) reinterpret_cast<float4*>(f32_row)[lane + 32 * i] = x[i];
     if (bf_row) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(x[i].x, x[i].y), hi = __floats2bfloat162_rn(x[i].z, x[i].w);
       uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      u.x = pack16<FP16>(x[i].x, x[i].y);
+      u.y = pack16<FP16>(x[i].z, x[i].w);
       reinterpret_cast<uint2*>(bf_row)[lane + 32 * i] = u;
     }
   }
@@ -126,7 +139,7 @@ __device__ __forceinline__ void store_row(const float4 (&x)[VEC], float* __restr
 // One warp per masked copy: derives every token id of the copy on the fly (ids never touch
 // HBM), gathers word + position + token_type(0) rows, LayerNorm, writes the fp32 residual
 // stream and the bf16 GEMM operand.
-template <int VEC>
+template <int VEC, bool FP16>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off, CopyPlan plan,
                 int32_t n_copies, const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
@@ -155,12 +168,12 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
     }
     ln_normalize<VEC>(x, g, b, eps, lane);
     const size_t row = (size_t)(start + p);
-    store_row<VEC>(x, hidden_f32 + row * H, hidden_bf16 + row * H, lane);
+    store_row<VEC, FP16>(x, hidden_f32 + row * H, hidden_bf16 + row * H, lane);
   }
 }
 
 // hidden = LayerNorm(y + hidden) in place (+ bf16 copy).  One warp per row.
-template <int VEC, bool RESID>
+template <int VEC, bool RESID, bool FP16>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ln_kernel(const float* __restrict__ y, float* __restrict__ hidden_f32, __nv_bfloat16* __restrict__ out_bf16,
           const float* __restrict__ g, const float* __restrict__ b, float eps, int64_t rows) {
@@ -181,7 +194,7 @@ ln_kernel(const float* __restrict__ y, float* __restrict__ hidden_f32, __nv_bflo
     }
   }
   ln_normalize<VEC>(x, g, b, eps, lane);
-  store_row<VEC>(x, RESID ? hidden_f32 + row * H : nullptr, out_bf16 + row * H, lane);
+  store_row<VEC, FP16>(x, RESID ? hidden_f32 + row * H : nullptr, out_bf16 + row * H, lane);
 }
 
 // ---------------------------------------------------------------- varlen self-attention
@@ -296,18 +309,23 @@ __global__ void attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfl
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_VROW = 72;   // bf16 elements per staged V row (144 B: conflict-free ldmatrix)
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+template <bool FP16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if constexpr (FP16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
 }
 
 // Streaming form: any T; V blocks staged per 16-key block, Q/K fragments straight from global.
+template <bool FP16>
 __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb, const __nv_bfloat16* __restrict__ kb,
                                             const __nv_bfloat16* __restrict__ vb, __nv_bfloat16* __restrict__ ob,
                                             int T, size_t ld, int H, int lane, __nv_bfloat16* vs) {
@@ -351,7 +369,7 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + 16 * ks);
           const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + 16 * ks + 8);
-          mma_bf16_16816(s[j], qf[ks], b0, b1);
+          mma_16816<FP16>(s[j], qf[ks], b0, b1);
         }
       }
       // mask keys >= T, scale into the log2 domain, online softmax (rows g and g+8)
@@ -383,8 +401,8 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
         const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
         l[0] += (p00 + p01) + (p10 + p11);
         l[1] += (p02 + p03) + (p12 + p13);
-        pf[0] = pack2_bf16(p00, p01); pf[1] = pack2_bf16(p02, p03);
-        pf[2] = pack2_bf16(p10, p11); pf[3] = pack2_bf16(p12, p13);
+        pf[0] = pack16<FP16>(p00, p01); pf[1] = pack16<FP16>(p02, p03);
+        pf[2] = pack16<FP16>(p10, p11); pf[3] = pack16<FP16>(p12, p13);
       }
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
@@ -400,8 +418,8 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
         uint32_t b0, b1, b2, b3;
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                      : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-        mma_bf16_16816(o[n], pf, b0, b1);
-        mma_bf16_16816(o[n + 1], pf, b2, b3);
+        mma_16816<FP16>(o[n], pf, b0, b1);
+        mma_16816<FP16>(o[n + 1], pf, b2, b3);
       }
     }
     // finish: row sums across the quad, normalise, store bf16
@@ -415,9 +433,9 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       if (q0 < T)
-        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][0] * inv0, o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack16<FP16>(o[n][0] * inv0, o[n][1] * inv0);
       if (q1 < T)
-        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][2] * inv1, o[n][3] * inv1);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack16<FP16>(o[n][2] * inv1, o[n][3] * inv1);
     }
   }
 }
@@ -428,6 +446,7 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
 constexpr int ATT_TS = 32;
 constexpr int ATT_STAGE_ELEMS = 3 * ATT_TS * ATT_VROW;   // bf16 elements per warp (13.5 KiB)
 
+template <bool FP16>
 __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb, __nv_bfloat16* __restrict__ ob, int T,
                                             size_t ld, int H, int lane, __nv_bfloat16* sm) {
   const int g = lane >> 2, cq = lane & 3;
@@ -468,8 +487,8 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
           uint32_t b0, b1, b2, b3;
           asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                        : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-          mma_bf16_16816(s[j], qf[2 * kp], b0, b1);
-          mma_bf16_16816(s[j], qf[2 * kp + 1], b2, b3);
+          mma_16816<FP16>(s[j], qf[2 * kp], b0, b1);
+          mma_16816<FP16>(s[j], qf[2 * kp + 1], b2, b3);
         }
       }
       float bm[2] = {-INFINITY, -INFINITY};
@@ -500,8 +519,8 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
         const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
         l[0] += (p00 + p01) + (p10 + p11);
         l[1] += (p02 + p03) + (p12 + p13);
-        pf[0] = pack2_bf16(p00, p01); pf[1] = pack2_bf16(p02, p03);
-        pf[2] = pack2_bf16(p10, p11); pf[3] = pack2_bf16(p12, p13);
+        pf[0] = pack16<FP16>(p00, p01); pf[1] = pack16<FP16>(p02, p03);
+        pf[2] = pack16<FP16>(p10, p11); pf[3] = pack16<FP16>(p12, p13);
       }
       if (k0 > 0) {
 #pragma unroll
@@ -515,8 +534,8 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
         uint32_t b0, b1, b2, b3;
         asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                      : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-        mma_bf16_16816(o[n], pf, b0, b1);
-        mma_bf16_16816(o[n + 1], pf, b2, b3);
+        mma_16816<FP16>(o[n], pf, b0, b1);
+        mma_16816<FP16>(o[n + 1], pf, b2, b3);
       }
     }
 #pragma unroll
@@ -529,13 +548,14 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       if (q0 < T)
-        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][0] * inv0, o[n][1] * inv0);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack16<FP16>(o[n][0] * inv0, o[n][1] * inv0);
       if (q1 < T)
-        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack2_bf16(o[n][2] * inv1, o[n][3] * inv1);
+        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack16<FP16>(o[n][2] * inv1, o[n][3] * inv1);
     }
   }
 }
 
+template <bool FP16>
 __global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
                      int32_t n_copies, int H, int NH) {
@@ -551,8 +571,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   const size_t ld = (size_t)3 * H;
   const __nv_bfloat16* qb = qkv + (size_t)start * ld + head * 64;
   __nv_bfloat16* ob = ctx + (size_t)start * H + head * 64;
-  if (T <= ATT_TS) attn_staged(qb, ob, T, ld, H, lane, sm);
-  else attn_stream(qb, qb + H, qb + 2 * H, ob, T, ld, H, lane, sm);
+  if (T <= ATT_TS) attn_staged<FP16>(qb, ob, T, ld, H, lane, sm);
+  else attn_stream<FP16>(qb, qb + H, qb + 2 * H, ob, T, ld, H, lane, sm);
 }
 
 // ---------------------------------------------------------------- head helpers
@@ -610,17 +630,20 @@ __global__ void hyp_sum_kernel(const float* __restrict__ tok_logp, const int32_t
   out_pll[h] = acc;
 }
 
+template <bool FP16>
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
     uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    u.x = pack16<FP16>(v.x, v.y);
+    u.y = pack16<FP16>(v.z, v.w);
     *reinterpret_cast<uint2*>(dst + i) = u;
   } else {
-    for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    for (int64_t j = i; j < n; ++j) {
+      if constexpr (FP16) reinterpret_cast<__half*>(dst)[j] = __float2half_rn(src[j]);
+      else dst[j] = __float2bfloat16_rn(src[j]);
+    }
   }
 }
 
@@ -658,47 +681,60 @@ int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPla
 int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                     const float* word_emb, const float* pos_emb, const float* type_emb, const float* g, const float* b,
                     float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id, float* hidden_f32,
-                    void* hidden_bf16, cudaStream_t s) {
+                    void* hidden_bf16, bool fp16, cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   const unsigned grid = (unsigned)ceil_div(n_copies, WARPS_PER_BLOCK);
-  PLLB_DISPATCH_VEC(H, (embed_ln_kernel<VEC><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
-                           tokens, hyp_tok_off, plan, n_copies, word_emb, pos_emb, type_emb, g, b, eps, cls_id, sep_id,
-                           mask_id, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_bf16))));
+#define EMB(F) embed_ln_kernel<VEC, F><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(                                         \
+      tokens, hyp_tok_off, plan, n_copies, word_emb, pos_emb, type_emb, g, b, eps, cls_id, sep_id, mask_id, hidden_f32, \
+      reinterpret_cast<__nv_bfloat16*>(hidden_bf16))
+  PLLB_DISPATCH_VEC(H, (fp16 ? EMB(true) : EMB(false)));
+#undef EMB
   PLLB_LAUNCH_CHECK("embed_ln_kernel");
   return PLLB_OK;
 }
 
 int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b, float eps,
-                       int64_t rows, int H, cudaStream_t s) {
+                       int64_t rows, int H, bool fp16, cudaStream_t s) {
   if (rows <= 0) return PLLB_OK;
   const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
-  PLLB_DISPATCH_VEC(H, (ln_kernel<VEC, true><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
-                           y, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_bf16), g, b, eps, rows)));
+#define LNR(F) ln_kernel<VEC, true, F><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(                                  \
+      y, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_bf16), g, b, eps, rows)
+  PLLB_DISPATCH_VEC(H, (fp16 ? LNR(true) : LNR(false)));
+#undef LNR
   PLLB_LAUNCH_CHECK("ln_kernel<resid>");
   return PLLB_OK;
 }
 
 int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const float* b, float eps, int64_t rows, int H,
-                         cudaStream_t s) {
+                         bool fp16, cudaStream_t s) {
   if (rows <= 0) return PLLB_OK;
   const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
-  PLLB_DISPATCH_VEC(H, (ln_kernel<VEC, false><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
-                           x, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), g, b, eps, rows)));
+#define LNP(F) ln_kernel<VEC, false, F><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(                                 \
+      x, nullptr, reinterpret_cast<__nv_bfloat16*>(out_bf16), g, b, eps, rows)
+  PLLB_DISPATCH_VEC(H, (fp16 ? LNP(true) : LNP(false)));
+#undef LNP
   PLLB_LAUNCH_CHECK("ln_kernel<plain>");
   return PLLB_OK;
 }
 
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH, int max_T,
-                     cudaStream_t s) {
+                     bool fp16, cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
   (void)max_T;
   const int64_t pairs = (int64_t)n_copies * NH;
   const int smem = ATT_WARPS * ATT_STAGE_ELEMS * 2;
-  PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  attention_mma_kernel<<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
-      NH);
+  if (fp16) {
+    PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_mma_kernel<true><<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
+        NH);
+  } else {
+    PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attention_mma_kernel<false><<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
+        NH);
+  }
   PLLB_LAUNCH_CHECK("attention_mma_kernel");
   return PLLB_OK;
 }
@@ -756,9 +792,11 @@ int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t 
   return PLLB_OK;
 }
 
-int launch_f32_to_bf16(const float* src, void* dst, int64_t n, cudaStream_t s) {
+int launch_f32_to_bf16(const float* src, void* dst, int64_t n, bool fp16, cudaStream_t s) {
   if (n <= 0) return PLLB_OK;
-  f32_to_bf16_kernel<<<(unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  const unsigned grid = (unsigned)ceil_div(ceil_div(n, 4), 256);
+  if (fp16) f32_to_bf16_kernel<true><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  else f32_to_bf16_kernel<false><<<grid, 256, 0, s>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   PLLB_LAUNCH_CHECK("f32_to_bf16_kernel");
   return PLLB_OK;
 }

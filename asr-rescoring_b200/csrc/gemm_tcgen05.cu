@@ -20,6 +20,7 @@
 //              and TMA stores; or, for the decoder, an online logsumexp over the vocab
 //              tile plus the label-column pick, so the [copies x V] logits never exist.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <mutex>
 
@@ -95,12 +96,19 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return ffma2(hx, e, hx);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// two fp32 -> one packed 16-bit pair in the operand dtype of the handle (bf16 or fp16)
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (FP16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
 }
 
-template <int EPI>
+template <int EPI, bool FP16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
@@ -169,7 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = FP16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
@@ -271,9 +279,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 4; ++j) v[j] = gelu_erf2(v[j]);
             }
             const uint32_t dst = buf + lane * 128 + ((c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16x2(v[0].x, v[0].y)),
-                         "r"(pack_bf16x2(v[1].x, v[1].y)), "r"(pack_bf16x2(v[2].x, v[2].y)),
-                         "r"(pack_bf16x2(v[3].x, v[3].y))
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack16x2<FP16>(v[0].x, v[0].y)),
+                         "r"(pack16x2<FP16>(v[1].x, v[1].y)), "r"(pack16x2<FP16>(v[2].x, v[2].y)),
+                         "r"(pack16x2<FP16>(v[3].x, v[3].y))
                          : "memory");
           }
           fence_proxy_async_smem();
@@ -367,23 +375,24 @@ int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_
   return PLLB_OK;
 }
 
-template <int EPI>
-int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
-               cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    PLLB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
-  }
-  gemm_tcgen05_kernel<EPI><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(a, b, c, kp);
+template <int EPI, bool FP16>
+int launch_epi2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
+                cudaStream_t stream) {
+  PLLB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  gemm_tcgen05_kernel<EPI, FP16><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(a, b, c, kp);
   PLLB_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return PLLB_OK;
+}
+template <int EPI>
+int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid, bool fp16,
+               cudaStream_t stream) {
+  return fp16 ? launch_epi2<EPI, true>(a, b, c, kp, grid, stream) : launch_epi2<EPI, false>(a, b, c, kp, grid, stream);
 }
 
 }  // namespace
 
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                        int epilogue, const LseArgs* lse, cudaStream_t stream) {
+                        int epilogue, const LseArgs* lse, bool fp16, cudaStream_t stream) {
   if (M <= 0) return PLLB_OK;
   if (N % BN != 0 || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm: need N % 256 == 0 and K % 64 == 0");
@@ -406,11 +415,11 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
   const int64_t tiles = ceil_div(M, BM) * (N / BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, stream);
-    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, stream);
-    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, stream);
-    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, stream);
+    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, fp16, stream);
+    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, fp16, stream);
+    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, fp16, stream);
+    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, fp16, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, fp16, stream);
   }
   return fail(PLLB_ERR_INVALID, "gemm: unknown epilogue");
 }

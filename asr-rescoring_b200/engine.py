@@ -27,7 +27,8 @@ class PllScorer:
     MLM_PLL/main.py:73-114,184-187."""
 
     def __init__(self, state_dict: Dict[str, "torch.Tensor"], cfg: Optional[dict] = None, device: int = 0,
-                 max_chunk_tokens: int = 0, cls_id: int = 101, sep_id: int = 102, mask_id: int = 103):
+                 max_chunk_tokens: int = 0, cls_id: int = 101, sep_id: int = 102, mask_id: int = 103,
+                 operand_dtype: str = "bf16"):
         import torch
         from .synth import config_from_state_dict
 
@@ -73,7 +74,9 @@ class PllScorer:
         w.decoder_w = dp(dec_w)
         w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
         d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
-                      self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id)
+                      self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id,
+                      {"bf16": 0, "fp16": 1}[operand_dtype])
+        self.operand_dtype = operand_dtype
         torch.cuda.synchronize(dev)
         check(self._lib.pllb_create(ctypes.byref(self._h), ctypes.byref(d), ctypes.byref(w), int(max_chunk_tokens), device))
         del keep   # the library made its own (bf16 / fp32) copies

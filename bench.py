@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-sample-hyps", type=int, default=400, help="hypotheses in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--operand-dtype", default="bf16", choices=["bf16", "fp16"])
     return ap.parse_args()
 
 
@@ -117,8 +118,9 @@ def cpu_port_hyps_per_s(cfg, sd, tok, off, n_hyps, threads=None):
     """The oracle port of the reference CPU path on the first n_hyps hypotheses."""
     import torch
     from oracle import pll_oracle
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    torch.set_num_threads(threads)
     hyps = {"u": {f"hyp_{i + 1}": [int(t) for t in tok[off[i]:off[i + 1]]] for i in range(n_hyps)}}
     t0 = time.perf_counter()
     pll_oracle.score_hyps(sd, cfg, hyps, batch_size=32)      # score.yaml:16 batch_size
@@ -142,6 +144,8 @@ def run_reference(args):
         return
     import torch
     from asr_rescoring_b200 import synth
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     n_utts, n_best, model, lo, hi = WORKLOADS[args.workload]
     cfg = model_cfg(model)
     nb = synth.make_nbest(max(args.cpu_sample_hyps // n_best + 1, 4), n_best, seed=0, min_len=lo, max_len=hi)
@@ -216,7 +220,7 @@ def main():
     W = len(weights)
 
     sd = synth.random_init_state_dict(cfg, 10)
-    scorer = engine.PllScorer(sd, cfg, device=local, max_chunk_tokens=args.chunk_tokens)
+    scorer = engine.PllScorer(sd, cfg, device=local, max_chunk_tokens=args.chunk_tokens, operand_dtype=args.operand_dtype)
 
     # device-resident inputs for `value`
     t = lambda a: torch.from_numpy(a).to(dev)
@@ -327,7 +331,7 @@ def main():
         out = {
             "metric": METRIC, "value": total_hyps / (ms_value / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
-            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16",
+            "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": args.operand_dtype,
             "data": "synthetic",
             "config": {"workload": args.workload, "model": model, "utterances_per_gpu": N, "n_best": n_best,
                        "hyps_per_gpu": n_hyp, "masked_copies_per_gpu": int(lens.sum()),

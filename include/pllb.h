@@ -51,6 +51,10 @@ typedef struct pllb_model_desc {
   int32_t max_position;   /* 512                                             */
   float   ln_eps;         /* 1e-12                                           */
   int32_t cls_id, sep_id, mask_id; /* 101, 102, 103                          */
+  int32_t operand_dtype;  /* GEMM / attention operand type, fp32 accumulate
+                             either way: 0 = bf16 (default), 1 = IEEE fp16
+                             (same tensor-core rate, 3 more mantissa bits:
+                             ~6x smaller PLL error, range 65504)            */
 } pllb_model_desc;
 
 /* One encoder layer; DEVICE pointers to fp32 tensors in nn.Linear layout

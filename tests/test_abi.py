@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.ModelDesc) == 40
+    assert ctypes.sizeof(_lib.ModelDesc) == 44
     assert ctypes.sizeof(_lib.LayerWeights) == 16 * 8
     assert ctypes.sizeof(_lib.Weights) == 12 * 8
     assert ctypes.sizeof(_lib.Stats) == 8 * 5 + 8 + 4 + 4 + 8

@@ -216,6 +216,18 @@ def test_pll_vs_reference_golden(gold_dir):
                     assert got[u][h] == 0 and isinstance(got[u][h], int)
 
 
+def test_pll_fp16_operand_mode_vs_reference_golden(gold_dir):
+    """operand_dtype="fp16": same kernels with IEEE-half operands; the error against the
+    reference drops ~6x (10 mantissa bits instead of 7)."""
+    gold = json.load(open(os.path.join(gold_dir, "pll_golden.json")))
+    for case in gold["cases"]:
+        sd = synth.random_init_state_dict(case["cfg"], case["seed"], case["perturb"])
+        with engine.PllScorer(sd, case["cfg"], operand_dtype="fp16") as sc:
+            got = sc.score_hyps(case["hyps"])
+        worst = max(abs(got[u][h] - v) for u, hs in case["pll"].items() for h, v in hs.items())
+        assert worst <= 0.012, (case["name"], worst)
+
+
 def test_pll_vs_live_oracle_and_rescored_one_best():
     cfg = synth.BERT_BASE_CHINESE
     sd = synth.random_init_state_dict(cfg, 10)

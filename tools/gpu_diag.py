@@ -206,9 +206,33 @@ def step_bench():
     print("pll sample", pll[:4], "finite", bool(np.isfinite(pll).all()))
 
 
+def step_numerics():
+    """Error distribution of the GPU path vs the fp32 oracle, bf16 and fp16 operands."""
+    import numpy as np
+    from oracle import pll_oracle
+    from asr_rescoring_b200 import engine, synth
+    cfg = synth.BERT_BASE_CHINESE
+    sd = synth.random_init_state_dict(cfg, 10, False)
+    nb = synth.make_nbest(int(os.environ.get("NUM_UTTS", "30")), 5, seed=321)
+    tok, off = nb.packed_tokens()
+    L = np.diff(off)
+    hyps = {"u": {f"hyp_{i + 1}": [int(t) for t in tok[off[i]:off[i + 1]]] for i in range(len(L))}}
+    t = time.time()
+    exp = pll_oracle.score_hyps(sd, cfg, hyps)
+    ref = np.array([exp["u"][f"hyp_{i + 1}"] for i in range(len(L))])
+    print(f"oracle: {len(L)} hyps in {time.time()-t:.1f}s")
+    for dt in ("bf16", "fp16"):
+        with engine.PllScorer(sd, cfg, operand_dtype=dt) as sc:
+            got = sc.score_packed(tok, off)
+        e = got - ref
+        print(f"{dt}: mean|e| {np.abs(e).mean():.4f} max|e| {np.abs(e).max():.4f} std {e.std():.4f} bias {e.mean():+.4f} "
+              f"per-sqrt(L) std {(e/np.sqrt(L)).std():.4f} frac>0.05 {np.mean(np.abs(e)>0.05):.4f} "
+              f"p99 {np.percentile(np.abs(e),99):.4f}")
+
+
 STEPS = {"lev": step_lev, "combiner": step_combiner, "expand": step_expand, "gemm_simt": step_gemm_simt,
          "gemm": step_gemm, "hidden": step_hidden, "hidden_base": lambda: step_hidden("base"), "pll": step_pll,
-         "bench": step_bench}
+         "bench": step_bench, "numerics": step_numerics}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:
