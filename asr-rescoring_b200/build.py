@@ -15,6 +15,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = {
     "api.cu": [],
     "gemm_tcgen05.cu": [],
+    "gemm_ln_tcgen05.cu": [],
     "encoder_kernels.cu": [],
     # fp64 combiner must round like numpy: no FMA contraction, IEEE division
     "rescore_kernels.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -54,6 +55,7 @@ struct pllb_context {
   pllb_model_desc d{};
   int device = 0;
   bool fp16 = false;                 // GEMM operand dtype: bf16 (default) or IEEE fp16
+  bool fused_ln = true;              // residual + LayerNorm inside the GEMM epilogue (PLLB_FUSED_LN=0 disables)
   int64_t cap_rows = 0, cap_copies = 0, cap_hyps = 0;
   int vocab_pad = 0, tiles_v = 0;
   std::vector<void*> owned;          // every cudaMalloc of this handle
@@ -147,6 +149,35 @@ int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const fl
   return PLLB_OK;
 }
 
+// GEMM + bias + residual + LayerNorm: fused kernel, or (PLLB_FUSED_LN=0) GEMM -> fp32 -> LayerNorm kernel.
+int timed_gemm_ln(pllb_context* c, int kind, const void* A, const void* W, const float* bias, const float* g,
+                  const float* be, float* hid32, void* hid16, int64_t M, int K, cudaStream_t s) {
+  const int H = c->d.hidden;
+  if (!c->fused_ln) {
+    RC(timed_gemm(c, kind, A, W, bias, c->y_f32, M, H, K, EPI_BIAS_F32, nullptr, s));
+    return launch_residual_ln(c->y_f32, hid32, hid16, g, be, c->d.ln_eps, M, H, c->fp16, s);
+  }
+  TimedLaunch* tl = nullptr;
+  if (c->timing) {
+    if (c->timed_used == c->timed.size()) {
+      TimedLaunch t{};
+      PLLB_CUDA(cudaEventCreate(&t.start));
+      PLLB_CUDA(cudaEventCreate(&t.stop));
+      c->timed.push_back(t);
+    }
+    tl = &c->timed[c->timed_used++];
+    tl->kind = kind;
+    PLLB_CUDA(cudaEventRecord(tl->start, s));
+  }
+  RC(launch_gemm_ln(A, W, bias, g, be, c->d.ln_eps, hid32, hid16, M, H, K, c->fp16, s));
+  if (tl) PLLB_CUDA(cudaEventRecord(tl->stop, s));
+  const double fl = 2.0 * (double)M * (double)H * (double)K;
+  c->stats.gemm_flops += fl;
+  c->gemm_flops_kind[kind] += fl;
+  c->stats.last_gemm_launches += 1;
+  return PLLB_OK;
+}
+
 // Encoder + head over one chunk whose metadata (tok_off / copy_base / row_base, each
 // n_hyp+1 int32) already sits in device memory.  upto_layer < 0: full scoring.
 int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, const int32_t* copy_base,
@@ -170,18 +201,14 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
     if (prune_last && l == n_layers - 1) {
       RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
       RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
-      RC(timed_gemm(c, G_AO, c->hg, L.ao_w, L.ao_b, c->y_f32, n_copies, H, H, EPI_BIAS_F32, nullptr, s));
-      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.ao_g, L.ao_be, d.ln_eps, n_copies, H, c->fp16, s));
+      RC(timed_gemm_ln(c, G_AO, c->hg, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hid_c, c->t_bf16, n_copies, H, s));
       RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
-      RC(timed_gemm(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, c->y_f32, n_copies, H, I, EPI_BIAS_F32, nullptr, s));
-      RC(launch_residual_ln(c->y_f32, c->hid_c, c->t_bf16, L.out_g, L.out_be, d.ln_eps, n_copies, H, c->fp16, s));
+      RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hid_c, c->t_bf16, n_copies, I, s));
       break;
     }
-    RC(timed_gemm(c, G_AO, c->ctx, L.ao_w, L.ao_b, c->y_f32, n_rows, H, H, EPI_BIAS_F32, nullptr, s));
-    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.ao_g, L.ao_be, d.ln_eps, n_rows, H, c->fp16, s));
+    RC(timed_gemm_ln(c, G_AO, c->ctx, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hidden_f32, c->hidden_bf16, n_rows, H, s));
     RC(timed_gemm(c, G_FF1, c->hidden_bf16, L.ff1_w, L.ff1_b, c->wide, n_rows, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
-    RC(timed_gemm(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, c->y_f32, n_rows, H, I, EPI_BIAS_F32, nullptr, s));
-    RC(launch_residual_ln(c->y_f32, c->hidden_f32, c->hidden_bf16, L.out_g, L.out_be, d.ln_eps, n_rows, H, c->fp16, s));
+    RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hidden_f32, c->hidden_bf16, n_rows, I, s));
   }
   if (upto_layer >= 0) return PLLB_OK;
   // MLM head at the masked row of every copy only (the reference evaluates all B*T rows,
@@ -386,6 +413,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   c->d = d;
   c->device = device;
   c->fp16 = d.operand_dtype == 1;
+  if (const char* e = getenv("PLLB_FUSED_LN")) c->fused_ln = atoi(e) != 0;
   cudaStream_t s = 0;
   const int H = d.hidden, I = d.intermediate, V = d.vocab;
   int rc = PLLB_OK;

@@ -56,6 +56,10 @@ struct LseArgs {
 // fp16 = operands (and 16-bit outputs) are IEEE half instead of bf16.
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                         int epilogue, const LseArgs* lse, bool fp16, cudaStream_t stream);
+// hidden_f32 = LayerNorm(A * W^T + bias + hidden_f32) in place, hidden_16 = 16-bit copy
+// (gemm_ln_tcgen05.cu: cluster of H/256 CTAs per 128-row block, row statistics through DSMEM).
+int launch_gemm_ln(const void* A, const void* W, const float* bias, const float* gamma, const float* beta, float eps,
+                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, bool fp16, cudaStream_t stream);
 int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                      int epilogue, cudaStream_t stream);
 

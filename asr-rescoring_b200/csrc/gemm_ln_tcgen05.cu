@@ -1,0 +1,518 @@
+// gemm_ln_tcgen05.cu — GEMM with the bias + residual + LayerNorm epilogue fused in:
+//
+//   hidden = LayerNorm(A[M,K] * W[H,K]^T + bias + hidden)          (in place, fp32)
+//   hidden16 = bf16/fp16(hidden)                                    (operand of the next GEMM)
+//
+// i.e. BertSelfOutput / BertOutput (transformers modeling_bert.py:294-298, 352-356) in one
+// kernel.  The separate LayerNorm kernel moves 10.5 KB per row and layer-half through HBM
+// (pre-LN fp32 out and back in, residual in, fp32 + 16-bit out); fused, the residual is
+// read once and the two outputs written once (7.5 KB), and the 3 KB pre-LN round trip
+// disappears.
+//
+// A LayerNorm row spans H = 768 / 1024 columns, more than the 512 fp32 TMEM columns one SM
+// owns, so a thread-block CLUSTER of CN = H/256 CTAs covers one 128-row block: CTA rank r
+// computes the 128x256 tile of columns [256r, 256r+256) with the same TMA -> tcgen05.mma ->
+// TMEM pipeline as gemm_tcgen05.cu; its epilogue warps pull the tile into registers (one row
+// per thread, 128 columns each), add bias and the residual (TMA-staged through swizzled
+// shared memory), reduce (mean, M2) per row inside the CTA, exchange the per-CTA pair with
+// the peer CTAs through distributed shared memory (st.shared::cluster + a cluster-scope
+// mbarrier), merge them with Chan's formula, normalise from registers and TMA-store both
+// outputs.  No second pass over TMEM or HBM.
+#include <cooperative_groups.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace pllb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 3;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_COLS = BN / 2;               // columns per epilogue thread
+constexpr int BOX_BYTES = 32 * 128;            // 32 rows x 128 B swizzled box
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_CN = 4;
+
+constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);       // 147456
+constexpr int SMEM_EPI = EPI_WARPS * 2 * BOX_BYTES;                        // 65536
+constexpr int SMEM_RED = 2 * 2 * BM * 4;                                   // sum / m2, two halves
+constexpr int SMEM_XCHG = 2 * MAX_CN * BM * 8;                             // [parity][rank][row] float2
+constexpr int SMEM_GB = 2 * BN * 4;                                        // gamma, beta slice
+constexpr int SMEM_BARS = 512;
+constexpr int SMEM_TOTAL = SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG + SMEM_GB + SMEM_BARS + 1024;
+
+struct LnParams {
+  int M, K, H;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float eps;
+};
+
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (FP16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) {
+      printf("pllb: cluster mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+
+// tcgen05.ld 32 lanes x 32 columns straight into x[OFF .. OFF+31] (no staging registers)
+#define PLLB_X(i) "=r"(xr[OFF + (i)])
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld_into(uint32_t taddr, uint32_t (&xr)[N]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : PLLB_X(0), PLLB_X(1), PLLB_X(2), PLLB_X(3), PLLB_X(4), PLLB_X(5), PLLB_X(6), PLLB_X(7), PLLB_X(8), PLLB_X(9),
+        PLLB_X(10), PLLB_X(11), PLLB_X(12), PLLB_X(13), PLLB_X(14), PLLB_X(15), PLLB_X(16), PLLB_X(17), PLLB_X(18),
+        PLLB_X(19), PLLB_X(20), PLLB_X(21), PLLB_X(22), PLLB_X(23), PLLB_X(24), PLLB_X(25), PLLB_X(26), PLLB_X(27),
+        PLLB_X(28), PLLB_X(29), PLLB_X(30), PLLB_X(31)
+      : "r"(taddr)
+      : "memory");
+}
+#undef PLLB_X
+
+template <int CN, bool FP16>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmH32, const __grid_constant__ CUtensorMap tmH16, const LnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);            // generic pointer to the aligned base
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t sEpi = smem_base + SMEM_PIPE;
+  const uint32_t sRed = sEpi + SMEM_EPI;
+  const uint32_t sXchg = sRed + SMEM_RED;
+  const uint32_t sGB = sXchg + SMEM_XCHG;
+  const uint32_t sBar = sGB + SMEM_GB;
+  float* red = reinterpret_cast<float*>(smem_gen + SMEM_PIPE + SMEM_EPI);                 // [2 kinds][2 halves][128]
+  float2* xchg = reinterpret_cast<float2*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED);   // [2][MAX_CN][128]
+  float* gb = reinterpret_cast<float*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG);  // gamma[256], beta[256]
+  const uint32_t bar_full = sBar;                         // STAGES
+  const uint32_t bar_empty = bar_full + 8 * STAGES;       // STAGES
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;      // 2
+  const uint32_t bar_tempty = bar_tfull + 16;             // 2
+  const uint32_t bar_x = bar_tempty + 16;                 // 2 (cluster exchange, per parity)
+  const uint32_t bar_r = bar_x + 16;                      // EPI_WARPS x 2 (residual boxes)
+  const uint32_t tmem_slot = bar_r + 8 * EPI_WARPS * 2;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = CN > 1 ? cluster_ctarank() : 0;
+  const int cluster = CN > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int n_clusters = CN > 1 ? (int)num_clusters_x() : (int)gridDim.x;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int num_kb = p.K / BK;
+  const int n0 = (int)rank * BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    prefetch_tensormap(&tmH32);
+    prefetch_tensormap(&tmH16);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_tfull + 8 * s, 1);
+        mbar_init(bar_tempty + 8 * s, EPI_WARPS);
+        mbar_init(bar_x + 8 * s, CN * BM);                 // every row-owner thread of every CTA arrives
+      }
+      for (int s = 0; s < EPI_WARPS * 2; ++s) mbar_init(bar_r + 8 * s, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  // gamma / beta slice of this CTA's 256 columns
+  for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {
+    gb[i] = p.gamma[n0 + i];
+    gb[BN + i] = p.beta[n0 + i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (CN > 1) cluster_sync_all();          // peers' barriers are initialised before any remote arrive
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
+        const int m0 = mb * BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m0);
+          tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = FP16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = sA + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = sB + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            tcgen05_mma_bf16(d_tmem, make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2),
+                             make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(bar_empty + 8 * stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit(bar_tfull + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int ew = warp - 2;
+    const int half = ew >> 2;                  // which 128 columns of the tile
+    const int cbase = half * EPI_COLS;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t buf[2] = {sEpi + (ew * 2 + 0) * BOX_BYTES, sEpi + (ew * 2 + 1) * BOX_BYTES};
+    const uint32_t rbar[2] = {bar_r + 8 * (ew * 2 + 0), bar_r + 8 * (ew * 2 + 1)};
+    uint32_t rphase[2] = {0, 0};
+    uint32_t acc = 0, acc_phase = 0, xpar = 0, xphase[2] = {0, 0};
+    const float inv_local = 1.0f / (float)BN, inv_h = 1.0f / (float)(CN * BN);
+
+    for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
+      const int m0 = mb * BM;
+      const int grow0 = m0 + q * 32;                         // first global row of this warp
+      // residual boxes 0,1 (32 rows x 32 fp32 each); overlaps the MMAs of this tile
+      if (lane == 0) {
+        tma_store_wait_read<0>();                            // output stores of the previous tile left the buffers
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          mbar_arrive_expect_tx(rbar[b], BOX_BYTES);
+          tma_load_2d(buf[b], &tmH32, rbar[b], n0 + cbase + 32 * b, grow0);
+        }
+      }
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
+
+      uint32_t xr[EPI_COLS];                                  // fp32 bit patterns: the row slice lives in registers
+      float sum = 0.f;
+      tmem_ld_into<0>(t_addr, xr);
+      tmem_ld_into<32>(t_addr + 32, xr);
+      tmem_ld_into<64>(t_addr + 64, xr);
+      tmem_ld_into<96>(t_addr + 96, xr);
+      tcgen05_wait_ld();
+      // accumulator drained into registers: hand it back to the MMA warp right away
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mbar_wait(rbar[j & 1], rphase[j & 1]);
+        rphase[j & 1] ^= 1;
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + cbase + 32 * j);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 res;
+          const uint32_t src = buf[j & 1] + lane * 128 + ((c ^ (lane & 7)) << 4);
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(res.x), "=f"(res.y), "=f"(res.z), "=f"(res.w) : "r"(src));
+          const float4 b = __ldg(bias4 + c);
+          const int i0 = 32 * j + 4 * c;
+          const float v0 = (__uint_as_float(xr[i0 + 0]) + b.x) + res.x;
+          const float v1 = (__uint_as_float(xr[i0 + 1]) + b.y) + res.y;
+          const float v2 = (__uint_as_float(xr[i0 + 2]) + b.z) + res.z;
+          const float v3 = (__uint_as_float(xr[i0 + 3]) + b.w) + res.w;
+          xr[i0 + 0] = __float_as_uint(v0); xr[i0 + 1] = __float_as_uint(v1);
+          xr[i0 + 2] = __float_as_uint(v2); xr[i0 + 3] = __float_as_uint(v3);
+          sum += (v0 + v1) + (v2 + v3);
+        }
+        if (j < 2) {                                         // refill this buffer with box j+2
+          __syncwarp();
+          if (lane == 0) {
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(rbar[j & 1], BOX_BYTES);
+            tma_load_2d(buf[j & 1], &tmH32, rbar[j & 1], n0 + cbase + 32 * (j + 2), grow0);
+          }
+        }
+      }
+      // ---- per-row statistics: local mean, local M2, then merge across the cluster
+      red[half * BM + row_in_tile] = sum;
+      epi_bar_sync();
+      const float mean_loc = (red[row_in_tile] + red[BM + row_in_tile]) * inv_local;
+      float m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < EPI_COLS; ++i) {
+        const float d = __uint_as_float(xr[i]) - mean_loc;
+        m2 = fmaf(d, d, m2);
+      }
+      red[2 * BM + half * BM + row_in_tile] = m2;
+      epi_bar_sync();
+      float mean = mean_loc;
+      float M2 = red[2 * BM + row_in_tile] + red[3 * BM + row_in_tile];
+      if constexpr (CN > 1) {
+        if (half == 0) {
+          const uint32_t slot = sXchg + (uint32_t)((xpar * MAX_CN + rank) * BM + row_in_tile) * 8;
+#pragma unroll
+          for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer) {
+            st_cluster_f32x2(mapa(slot, peer), mean_loc, M2);
+            mbar_arrive_remote(mapa(bar_x + 8 * xpar, peer));
+          }
+        }
+        mbar_wait_cluster(bar_x + 8 * xpar, xphase[xpar]);
+        xphase[xpar] ^= 1;
+        float msum = 0.f;
+        float2 st[CN];
+#pragma unroll
+        for (int r2 = 0; r2 < CN; ++r2) {
+          st[r2] = xchg[(xpar * MAX_CN + r2) * BM + row_in_tile];
+          msum += st[r2].x;
+        }
+        mean = msum * (1.0f / CN);
+        M2 = 0.f;
+#pragma unroll
+        for (int r2 = 0; r2 < CN; ++r2) {
+          const float d = st[r2].x - mean;
+          M2 += st[r2].y + (float)BN * d * d;                // Chan et al. pairwise merge
+        }
+        xpar ^= 1;
+      }
+      const float rstd = rsqrtf(M2 * inv_h + p.eps);
+
+      // ---- normalise from registers, stage and store fp32 (in place) + 16-bit copies
+      int nstore = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t b32 = buf[nstore & 1];
+        if (lane == 0 && nstore >= 2) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gb + cbase + 32 * j + 4 * c);
+          const float4 b4 = *reinterpret_cast<const float4*>(gb + BN + cbase + 32 * j + 4 * c);
+          const int i0 = 32 * j + 4 * c;
+          xr[i0 + 0] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 0]) - mean) * rstd, g4.x, b4.x));
+          xr[i0 + 1] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 1]) - mean) * rstd, g4.y, b4.y));
+          xr[i0 + 2] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 2]) - mean) * rstd, g4.z, b4.z));
+          xr[i0 + 3] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 3]) - mean) * rstd, g4.w, b4.w));
+          const uint32_t dst = b32 + lane * 128 + ((c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(xr[i0 + 0]), "r"(xr[i0 + 1]),
+                       "r"(xr[i0 + 2]), "r"(xr[i0 + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmH32, b32, n0 + cbase + 32 * j, grow0);
+          tma_store_commit();
+        }
+        ++nstore;
+        if (j & 1) {                                         // 64 normalised columns ready: 16-bit box
+          const uint32_t b16 = buf[nstore & 1];
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int i0 = 32 * (j - 1) + 8 * c;
+            const uint32_t dst = b16 + lane * 128 + ((c ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 0]), __uint_as_float(xr[i0 + 1]))),
+                         "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 2]), __uint_as_float(xr[i0 + 3]))),
+                         "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 4]), __uint_as_float(xr[i0 + 5]))),
+                         "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 6]), __uint_as_float(xr[i0 + 7])))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmH16, b16, n0 + cbase + 32 * (j - 1), grow0);
+            tma_store_commit();
+          }
+          ++nstore;
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (CN > 1) cluster_sync_all();          // no CTA leaves while a peer may still address its shared memory
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int tmap2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt, uint64_t rows, uint64_t cols,
+           uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * (uint64_t)elt};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+  return PLLB_OK;
+}
+
+template <int CN, bool FP16>
+int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t32, const CUtensorMap& t16,
+              const LnParams& lp, int64_t tiles_m, cudaStream_t stream) {
+  auto kern = gemm_ln_kernel<CN, FP16>;
+  PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CN;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent: as many clusters as can be co-resident (clusters must fit inside a GPC)
+  static thread_local int max_clusters[MAX_CN + 1][2] = {};
+  int& mc = max_clusters[CN][FP16 ? 1 : 0];
+  if (mc == 0) {
+    cfg.gridDim = dim3(CN * (sm_count() / CN));
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sm_count() / CN;
+    }
+    mc = n;
+  }
+  const int clusters = (int)(tiles_m < mc ? tiles_m : mc);
+  cfg.gridDim = dim3(CN * clusters);
+  PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t32, t16, lp));
+  ++g_launch_counter;
+  return PLLB_OK;
+}
+
+}  // namespace
+
+int launch_gemm_ln(const void* A, const void* W, const float* bias, const float* gamma, const float* beta, float eps,
+                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, bool fp16, cudaStream_t stream) {
+  if (M <= 0) return PLLB_OK;
+  if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
+    return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
+  CUtensorMap ta, tb, t32, t16;
+  int rc;
+  if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
+  if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, BN, BK))) return rc;
+  if ((rc = tmap2d(&t32, hidden_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)H, 32, 32))) return rc;
+  if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
+  LnParams lp{(int)M, K, H, bias, gamma, beta, eps};
+  const int64_t tiles_m = ceil_div(M, BM);
+  switch (H / BN) {
+    case 1: return fp16 ? launch_cn<1, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<1, false>(ta, tb, t32, t16, lp, tiles_m, stream);
+    case 2: return fp16 ? launch_cn<2, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<2, false>(ta, tb, t32, t16, lp, tiles_m, stream);
+    case 3: return fp16 ? launch_cn<3, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<3, false>(ta, tb, t32, t16, lp, tiles_m, stream);
+    case 4: return fp16 ? launch_cn<4, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<4, false>(ta, tb, t32, t16, lp, tiles_m, stream);
+  }
+  return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported hidden size");
+}
+
+}  // namespace pllb

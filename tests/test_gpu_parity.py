@@ -186,6 +186,31 @@ def test_embeddings_and_layers_vs_oracle():
             assert err.max().item() < 0.03 and err.mean().item() < 3e-3   # bf16 GEMM operands
 
 
+@pytest.mark.parametrize("hidden", [256, 512, 768, 1024])
+def test_fused_gemm_layernorm_cluster_sizes(hidden):
+    """The residual+LayerNorm epilogue runs on a cluster of hidden/256 CTAs that exchange row
+    statistics through distributed shared memory: every cluster size against the fp32 oracle,
+    with a row count that is not a multiple of the 128-row tile and several tiles per cluster."""
+    cfg = dict(num_layers=2, hidden=hidden, num_heads=hidden // 64, intermediate=2 * hidden, vocab=1200,
+               max_position=64, type_vocab=2, ln_eps=1e-12)
+    sd = synth.random_init_state_dict(cfg, 21, perturb=True)
+    rng = np.random.default_rng(hidden)
+    lens = [int(x) for x in rng.integers(1, 40, size=60)]
+    off = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = rng.integers(104, cfg["vocab"], size=int(off[-1])).astype(np.int32)
+    with engine.PllScorer(sd, cfg) as sc:
+        got = sc.hidden(tok[:off[8]], off[:9], 2)
+        pll = sc.score_packed(tok, off)
+    exp = _oracle_hidden(sd, cfg, tok[:off[8]], off[:9], 2)
+    err = (got - exp).abs()
+    assert err.max().item() < 0.04 and err.mean().item() < 4e-3, (err.max().item(), err.mean().item())
+    hyps = {"u": {f"hyp_{i + 1}": [int(t) for t in tok[off[i]:off[i + 1]]] for i in range(12)}}
+    ref = pll_oracle.score_hyps(sd, cfg, hyps)
+    for i in range(12):
+        assert abs(pll[i] - ref["u"][f"hyp_{i + 1}"]) <= PLL_TOL
+
+
 def test_attention_paths_short_and_long_sequences():
     """T <= 32 takes the cp.async-staged attention path, longer sequences the streaming one;
     both against the fp32 oracle after one full layer, incl. T = 3 and T = max_position."""
