@@ -312,9 +312,7 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
     RC(run_chunk(c, hyp_tokens + (ch.tok_begin - off[0]), tok_off, copy_base, row_base, ch.n_hyp, ch.n_copies, ch.n_rows,
                  ch.max_T, out_pll ? out_pll + ch.hyp_begin : nullptr,
                  out_tok_logp ? out_tok_logp + (ch.tok_begin - off[0]) : nullptr, upto_layer, s));
-    if (out_hidden)
-      PLLB_CUDA(cudaMemcpyAsync(out_hidden, c->hidden_f32, sizeof(float) * ch.n_rows * c->d.hidden,
-                                cudaMemcpyDeviceToDevice, s));
+    if (out_hidden) RC(launch_t32_to_rowmajor(c->hidden_f32, out_hidden, ch.n_rows, c->d.hidden, s));
     c->stats.chunks += 1;
     c->stats.hyps_scored += ch.n_hyp;
     c->stats.copies_scored += ch.n_copies;
@@ -488,7 +486,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   TRY(dev_alloc(c, &c->plan.hyp, C));
   TRY(dev_alloc(c, &c->hg, C * H));
   TRY(dev_alloc(c, &c->t_f32, C * H));
-  TRY(dev_alloc(c, &c->hid_c, C * H));
+  TRY(dev_alloc(c, &c->hid_c, align_up(C, 128) * H));
   TRY(dev_alloc(c, &c->t_bf16, C * H));
   TRY(dev_alloc(c, &c->partials, C * c->tiles_v * 2));
   TRY(dev_alloc(c, &c->label_logit, C));

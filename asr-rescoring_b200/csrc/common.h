@@ -63,6 +63,19 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
 int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                      int epilogue, cudaStream_t stream);
 
+// ---- fp32 residual stream layout ("T32") ----------------------------------------
+// The fp32 hidden states are private to this library, so they are stored in the layout the
+// fused GEMM+LayerNorm epilogue wants: rows in blocks of 32; inside a block the 16-byte
+// groups of 4 columns of the 32 rows are contiguous:
+//     float index of (row, col) = ((row/32 * H/4 + col/4) * 32 + row%32) * 4 + col%4
+// A thread that owns one row (the TMEM register layout) then reads / writes consecutive
+// 16-byte pieces together with its 31 warp neighbours: 512 contiguous bytes per access.
+// Buffers are padded to a multiple of 32 rows.  The 16-bit operand copies stay row-major
+// (they are TMA-loaded as GEMM A operands).
+__host__ __device__ inline size_t t32_index(int64_t row, int col, int H) {
+  return (((size_t)(row >> 5) * (size_t)(H >> 2) + (size_t)(col >> 2)) * 32 + (size_t)(row & 31)) * 4 + (size_t)(col & 3);
+}
+
 // ---- encoder pieces (encoder_kernels.cu) -------------------------------------
 struct CopyPlan {          // device arrays, one entry per masked copy of the chunk
   int32_t* seq_start;      // first packed row of the copy
@@ -98,6 +111,8 @@ int launch_lse_finish(const float2* partials, const float* label_logit, int32_t 
                       float* tok_logp, cudaStream_t s);
 int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,
                    float* out_tok_logp, cudaStream_t s);
+// T32 blocked fp32 [rows, H] -> row-major fp32 (debug / parity output)
+int launch_t32_to_rowmajor(const float* src, float* dst, int64_t rows, int H, cudaStream_t s);
 int launch_f32_to_bf16(const float* src, void* dst, int64_t n, bool fp16, cudaStream_t s);
 
 // ---- combiner (rescore_kernels.cu, compiled with -fmad=false) ------------------

@@ -120,12 +120,18 @@ __device__ __forceinline__ void ln_normalize(float4 (&x)[VEC], const float* __re
   }
 }
 
+// fp32 goes to the T32 blocked layout (common.h): f32_base + row -> 16-byte group g of the row
+// sits at ((row/32 * H/4 + g) * 32 + row%32) float4s; the 16-bit copy is row-major.
+template <int VEC>
+__device__ __forceinline__ float4* t32_row(float* base, int64_t row) {
+  return reinterpret_cast<float4*>(base) + (size_t)(row >> 5) * (32 * VEC) * 32 + (row & 31);
+}
 template <int VEC, bool FP16>
-__device__ __forceinline__ void store_row(const float4 (&x)[VEC], float* __restrict__ f32_row,
+__device__ __forceinline__ void store_row(const float4 (&x)[VEC], float4* __restrict__ f32_t32,
                                           __nv_bfloat16* __restrict__ bf_row, int lane) {
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    if (f32_row) reinterpret_cast<float4*>(f32_row)[lane + 32 * i] = x[i];
+    if (f32_t32) f32_t32[(size_t)(lane + 32 * i) * 32] = x[i];
     if (bf_row) {
       uint2 u;
       u.x = pack16<FP16>(x[i].x, x[i].y);
@@ -168,7 +174,7 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
     }
     ln_normalize<VEC>(x, g, b, eps, lane);
     const size_t row = (size_t)(start + p);
-    store_row<VEC, FP16>(x, hidden_f32 + row * H, hidden_bf16 + row * H, lane);
+    store_row<VEC, FP16>(x, t32_row<VEC>(hidden_f32, (int64_t)row), hidden_bf16 + row * H, lane);
   }
 }
 
@@ -186,15 +192,15 @@ ln_kernel(const float* __restrict__ y, float* __restrict__ hidden_f32, __nv_bflo
 #pragma unroll
   for (int i = 0; i < VEC; ++i) x[i] = yr[lane + 32 * i];
   if (RESID) {
-    const float4* hr = reinterpret_cast<const float4*>(hidden_f32 + row * H);
+    const float4* hr = t32_row<VEC>(hidden_f32, row);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const float4 r = hr[lane + 32 * i];
+      const float4 r = hr[(size_t)(lane + 32 * i) * 32];
       x[i].x += r.x; x[i].y += r.y; x[i].z += r.z; x[i].w += r.w;
     }
   }
   ln_normalize<VEC>(x, g, b, eps, lane);
-  store_row<VEC, FP16>(x, RESID ? hidden_f32 + row * H : nullptr, out_bf16 + row * H, lane);
+  store_row<VEC, FP16>(x, RESID ? t32_row<VEC>(hidden_f32, row) : nullptr, out_bf16 + row * H, lane);
 }
 
 // ---------------------------------------------------------------- varlen self-attention
@@ -591,9 +597,22 @@ __global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int3
   const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= n) return;
-  const float4* s = reinterpret_cast<const float4*>(src + (size_t)rows[c] * H);
-  float4* d = reinterpret_cast<float4*>(dst + (size_t)c * H);
-  for (int i = lane; i < H / 4; i += 32) d[i] = s[i];
+  // both sides in the T32 blocked layout
+  const int64_t sr = rows[c];
+  const int G = H / 4;
+  const float4* s = reinterpret_cast<const float4*>(src) + (size_t)(sr >> 5) * G * 32 + (sr & 31);
+  float4* d = reinterpret_cast<float4*>(dst) + (size_t)(c >> 5) * G * 32 + (c & 31);
+  for (int i = lane; i < G; i += 32) d[(size_t)i * 32] = s[(size_t)i * 32];
+}
+
+__global__ void t32_to_rowmajor_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int H) {
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int G = H / 4;
+  const float4* s = reinterpret_cast<const float4*>(src) + (size_t)(row >> 5) * G * 32 + (row & 31);
+  float4* d = reinterpret_cast<float4*>(dst + row * H);
+  for (int i = lane; i < G; i += 32) d[i] = s[(size_t)i * 32];
 }
 
 // log_softmax(logits)[label] = label_logit - (max + log(sum exp)) — MLM_PLL/main.py:101-105
@@ -789,6 +808,13 @@ int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t 
   if (n_hyp <= 0) return PLLB_OK;
   hyp_sum_kernel<<<(unsigned)ceil_div(n_hyp, 128), 128, 0, s>>>(tok_logp, hyp_copy_base, n_hyp, out_pll, out_tok_logp);
   PLLB_LAUNCH_CHECK("hyp_sum_kernel");
+  return PLLB_OK;
+}
+
+int launch_t32_to_rowmajor(const float* src, float* dst, int64_t rows, int H, cudaStream_t s) {
+  if (rows <= 0) return PLLB_OK;
+  t32_to_rowmajor_kernel<<<(unsigned)ceil_div(rows, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(src, dst, rows, H);
+  PLLB_LAUNCH_CHECK("t32_to_rowmajor_kernel");
   return PLLB_OK;
 }
 

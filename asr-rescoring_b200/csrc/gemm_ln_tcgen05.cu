@@ -13,11 +13,11 @@
 // owns, so a thread-block CLUSTER of CN = H/256 CTAs covers one 128-row block: CTA rank r
 // computes the 128x256 tile of columns [256r, 256r+256) with the same TMA -> tcgen05.mma ->
 // TMEM pipeline as gemm_tcgen05.cu; its epilogue warps pull the tile into registers (one row
-// per thread, 128 columns each), add bias and the residual (TMA-staged through swizzled
-// shared memory), reduce (mean, M2) per row inside the CTA, exchange the per-CTA pair with
+// per thread, 128 columns each), add bias and the residual (read straight from the T32
+// blocked fp32 layout, fully coalesced), reduce (mean, M2) per row inside the CTA, exchange the per-CTA pair with
 // the peer CTAs through distributed shared memory (st.shared::cluster + a cluster-scope
-// mbarrier), merge them with Chan's formula, normalise from registers and TMA-store both
-// outputs.  No second pass over TMEM or HBM.
+// mbarrier), merge them with Chan's formula, normalise from registers, write the fp32 stream
+// back in place and TMA-store the 16-bit operand copy.  No second pass over TMEM or HBM.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -53,6 +53,7 @@ constexpr int SMEM_TOTAL = SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG + SMEM_GB
 
 struct LnParams {
   int M, K, H;
+  float* hidden;          // fp32 residual stream, T32 blocked layout, updated in place
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -106,10 +107,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "selp.b32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) break;
-    if (++spins > (1u << 26)) {
-      printf("pllb: cluster mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
@@ -133,11 +131,29 @@ __device__ __forceinline__ void tmem_ld_into(uint32_t taddr, uint32_t (&xr)[N]) 
       : "memory");
 }
 #undef PLLB_X
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// ordered (volatile) loads: keeps ptxas from hoisting a tile's worth of parameter loads above
+// the 128-register row slice and spilling it
+__device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4_ordered(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 template <int CN, bool FP16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmH32, const __grid_constant__ CUtensorMap tmH16, const LnParams p) {
+               const __grid_constant__ CUtensorMap tmH16, const LnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
@@ -173,7 +189,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
-    prefetch_tensormap(&tmH32);
     prefetch_tensormap(&tmH16);
   }
   if (warp == 1) {
@@ -187,7 +202,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(bar_tempty + 8 * s, EPI_WARPS);
         mbar_init(bar_x + 8 * s, CN * BM);                 // every row-owner thread of every CTA arrives
       }
-      for (int s = 0; s < EPI_WARPS * 2; ++s) mbar_init(bar_r + 8 * s, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -247,76 +261,66 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------------------------------------------------------- epilogue
+    // The fp32 residual stream is stored in the "T32" blocked layout (see common.h): inside a
+    // 32-row block the 16-byte column groups of the 32 rows are contiguous, so thread
+    // (row = lane) reading column group g touches base + ((blk * H/4 + g) * 32 + lane) * 16:
+    // every warp access is one fully coalesced 512-byte segment, straight between global memory
+    // and the registers that mirror the TMEM layout (row per thread) — no shared-memory staging
+    // and no dependent TMA round trips for the residual in / fp32 out traffic.
     const int q = warp & 3;                    // TMEM lane quarter
     const int ew = warp - 2;
     const int half = ew >> 2;                  // which 128 columns of the tile
     const int cbase = half * EPI_COLS;
     const int row_in_tile = q * 32 + lane;
     const uint32_t buf[2] = {sEpi + (ew * 2 + 0) * BOX_BYTES, sEpi + (ew * 2 + 1) * BOX_BYTES};
-    const uint32_t rbar[2] = {bar_r + 8 * (ew * 2 + 0), bar_r + 8 * (ew * 2 + 1)};
-    uint32_t rphase[2] = {0, 0};
     uint32_t acc = 0, acc_phase = 0, xpar = 0, xphase[2] = {0, 0};
     const float inv_local = 1.0f / (float)BN, inv_h = 1.0f / (float)(CN * BN);
+    const int groups_per_row = p.H >> 2;
+    const int g0 = (n0 + cbase) >> 2;          // first 4-column group of this thread
 
     for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
       const int m0 = mb * BM;
       const int grow0 = m0 + q * 32;                         // first global row of this warp
-      // residual boxes 0,1 (32 rows x 32 fp32 each); overlaps the MMAs of this tile
-      if (lane == 0) {
-        tma_store_wait_read<0>();                            // output stores of the previous tile left the buffers
+      float4* hrow = reinterpret_cast<float4*>(p.hidden) + ((size_t)(grow0 >> 5) * groups_per_row + g0) * 32 + lane;
+
+      // residual slice (32 x float4 per thread): issued before the accumulator is ready, so the
+      // loads fly while the tensor core is still working on this tile
+      uint32_t xr[EPI_COLS];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          mbar_arrive_expect_tx(rbar[b], BOX_BYTES);
-          tma_load_2d(buf[b], &tmH32, rbar[b], n0 + cbase + 32 * b, grow0);
-        }
+      for (int i = 0; i < EPI_COLS / 4; ++i) {
+        const float4 v = hrow[(size_t)i * 32];
+        xr[4 * i + 0] = __float_as_uint(v.x); xr[4 * i + 1] = __float_as_uint(v.y);
+        xr[4 * i + 2] = __float_as_uint(v.z); xr[4 * i + 3] = __float_as_uint(v.w);
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tcgen05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
-
-      uint32_t xr[EPI_COLS];                                  // fp32 bit patterns: the row slice lives in registers
       float sum = 0.f;
-      tmem_ld_into<0>(t_addr, xr);
-      tmem_ld_into<32>(t_addr + 32, xr);
-      tmem_ld_into<64>(t_addr + 64, xr);
-      tmem_ld_into<96>(t_addr + 96, xr);
-      tcgen05_wait_ld();
-      // accumulator drained into registers: hand it back to the MMA warp right away
+#pragma unroll
+      for (int j = 0; j < EPI_COLS / 8; ++j) {
+        uint32_t t[8];
+        tmem_ld_x8(t_addr + 8 * j, t);
+        tcgen05_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float4 b = ldg_f4_ordered(p.bias + n0 + cbase + 8 * j + 4 * c);
+          const int i0 = 8 * j + 4 * c;
+          const float v0 = (__uint_as_float(t[4 * c + 0]) + b.x) + __uint_as_float(xr[i0 + 0]);
+          const float v1 = (__uint_as_float(t[4 * c + 1]) + b.y) + __uint_as_float(xr[i0 + 1]);
+          const float v2 = (__uint_as_float(t[4 * c + 2]) + b.z) + __uint_as_float(xr[i0 + 2]);
+          const float v3 = (__uint_as_float(t[4 * c + 3]) + b.w) + __uint_as_float(xr[i0 + 3]);
+          xr[i0 + 0] = __float_as_uint(v0); xr[i0 + 1] = __float_as_uint(v1);
+          xr[i0 + 2] = __float_as_uint(v2); xr[i0 + 3] = __float_as_uint(v3);
+          sum += (v0 + v1) + (v2 + v3);
+        }
+      }
+      // accumulator drained into registers: hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        mbar_wait(rbar[j & 1], rphase[j & 1]);
-        rphase[j & 1] ^= 1;
-        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + cbase + 32 * j);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 res;
-          const uint32_t src = buf[j & 1] + lane * 128 + ((c ^ (lane & 7)) << 4);
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(res.x), "=f"(res.y), "=f"(res.z), "=f"(res.w) : "r"(src));
-          const float4 b = __ldg(bias4 + c);
-          const int i0 = 32 * j + 4 * c;
-          const float v0 = (__uint_as_float(xr[i0 + 0]) + b.x) + res.x;
-          const float v1 = (__uint_as_float(xr[i0 + 1]) + b.y) + res.y;
-          const float v2 = (__uint_as_float(xr[i0 + 2]) + b.z) + res.z;
-          const float v3 = (__uint_as_float(xr[i0 + 3]) + b.w) + res.w;
-          xr[i0 + 0] = __float_as_uint(v0); xr[i0 + 1] = __float_as_uint(v1);
-          xr[i0 + 2] = __float_as_uint(v2); xr[i0 + 3] = __float_as_uint(v3);
-          sum += (v0 + v1) + (v2 + v3);
-        }
-        if (j < 2) {                                         // refill this buffer with box j+2
-          __syncwarp();
-          if (lane == 0) {
-            fence_proxy_async_smem();
-            mbar_arrive_expect_tx(rbar[j & 1], BOX_BYTES);
-            tma_load_2d(buf[j & 1], &tmH32, rbar[j & 1], n0 + cbase + 32 * (j + 2), grow0);
-          }
-        }
-      }
+
       // ---- per-row statistics: local mean, local M2, then merge across the cluster
       red[half * BM + row_in_tile] = sum;
       epi_bar_sync();
@@ -360,56 +364,40 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const float rstd = rsqrtf(M2 * inv_h + p.eps);
 
-      // ---- normalise from registers, stage and store fp32 (in place) + 16-bit copies
-      int nstore = 0;
+      // ---- normalise in registers; fp32 goes straight back (coalesced, in place), the 16-bit
+      //      operand copy is row-major for the next GEMM's TMA: two swizzled boxes + TMA stores
+      if (lane == 0) tma_store_wait_read<0>();               // previous tile's boxes left the staging buffers
+      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t b32 = buf[nstore & 1];
-        if (lane == 0 && nstore >= 2) tma_store_wait_read<1>();
-        __syncwarp();
+      for (int i = 0; i < EPI_COLS / 4; ++i) {
+        const float4 g4 = lds_f4_ordered(sGB + (uint32_t)(cbase + 4 * i) * 4);
+        const float4 b4 = lds_f4_ordered(sGB + (uint32_t)(BN + cbase + 4 * i) * 4);
+        float4 y;
+        y.x = fmaf((__uint_as_float(xr[4 * i + 0]) - mean) * rstd, g4.x, b4.x);
+        y.y = fmaf((__uint_as_float(xr[4 * i + 1]) - mean) * rstd, g4.y, b4.y);
+        y.z = fmaf((__uint_as_float(xr[4 * i + 2]) - mean) * rstd, g4.z, b4.z);
+        y.w = fmaf((__uint_as_float(xr[4 * i + 3]) - mean) * rstd, g4.w, b4.w);
+        hrow[(size_t)i * 32] = y;
+        xr[2 * i + 0] = pack16x2<FP16>(y.x, y.y);            // compact in place: 2 packed words per group
+        xr[2 * i + 1] = pack16x2<FP16>(y.z, y.w);
+      }
+#pragma unroll
+      for (int bx = 0; bx < 2; ++bx) {                       // box bx: columns cbase + 64*bx .. +63
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gb + cbase + 32 * j + 4 * c);
-          const float4 b4 = *reinterpret_cast<const float4*>(gb + BN + cbase + 32 * j + 4 * c);
-          const int i0 = 32 * j + 4 * c;
-          xr[i0 + 0] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 0]) - mean) * rstd, g4.x, b4.x));
-          xr[i0 + 1] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 1]) - mean) * rstd, g4.y, b4.y));
-          xr[i0 + 2] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 2]) - mean) * rstd, g4.z, b4.z));
-          xr[i0 + 3] = __float_as_uint(fmaf((__uint_as_float(xr[i0 + 3]) - mean) * rstd, g4.w, b4.w));
-          const uint32_t dst = b32 + lane * 128 + ((c ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(xr[i0 + 0]), "r"(xr[i0 + 1]),
-                       "r"(xr[i0 + 2]), "r"(xr[i0 + 3])
+          const int w0 = 32 * bx + 4 * c;
+          const uint32_t dst = buf[bx] + lane * 128 + ((c ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(xr[w0 + 0]), "r"(xr[w0 + 1]),
+                       "r"(xr[w0 + 2]), "r"(xr[w0 + 3])
                        : "memory");
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmH32, b32, n0 + cbase + 32 * j, grow0);
-          tma_store_commit();
-        }
-        ++nstore;
-        if (j & 1) {                                         // 64 normalised columns ready: 16-bit box
-          const uint32_t b16 = buf[nstore & 1];
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int i0 = 32 * (j - 1) + 8 * c;
-            const uint32_t dst = b16 + lane * 128 + ((c ^ (lane & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 0]), __uint_as_float(xr[i0 + 1]))),
-                         "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 2]), __uint_as_float(xr[i0 + 3]))),
-                         "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 4]), __uint_as_float(xr[i0 + 5]))),
-                         "r"(pack16x2<FP16>(__uint_as_float(xr[i0 + 6]), __uint_as_float(xr[i0 + 7])))
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmH16, b16, n0 + cbase + 32 * (j - 1), grow0);
-            tma_store_commit();
-          }
-          ++nstore;
-        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmH16, buf[0], n0 + cbase, grow0);
+        tma_store_2d(&tmH16, buf[1], n0 + cbase + 64, grow0);
+        tma_store_commit();
       }
     }
     if (lane == 0) tma_store_wait_all();
@@ -456,7 +444,7 @@ int tmap2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt, ui
 }
 
 template <int CN, bool FP16>
-int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t32, const CUtensorMap& t16,
+int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t16,
               const LnParams& lp, int64_t tiles_m, cudaStream_t stream) {
   auto kern = gemm_ln_kernel<CN, FP16>;
   PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
@@ -486,7 +474,7 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   }
   const int clusters = (int)(tiles_m < mc ? tiles_m : mc);
   cfg.gridDim = dim3(CN * clusters);
-  PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t32, t16, lp));
+  PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t16, lp));
   ++g_launch_counter;
   return PLLB_OK;
 }
@@ -498,19 +486,18 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   if (M <= 0) return PLLB_OK;
   if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
-  CUtensorMap ta, tb, t32, t16;
+  CUtensorMap ta, tb, t16;
   int rc;
   if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
   if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, BN, BK))) return rc;
-  if ((rc = tmap2d(&t32, hidden_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)H, 32, 32))) return rc;
   if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
-  LnParams lp{(int)M, K, H, bias, gamma, beta, eps};
+  LnParams lp{(int)M, K, H, hidden_f32, bias, gamma, beta, eps};
   const int64_t tiles_m = ceil_div(M, BM);
   switch (H / BN) {
-    case 1: return fp16 ? launch_cn<1, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<1, false>(ta, tb, t32, t16, lp, tiles_m, stream);
-    case 2: return fp16 ? launch_cn<2, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<2, false>(ta, tb, t32, t16, lp, tiles_m, stream);
-    case 3: return fp16 ? launch_cn<3, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<3, false>(ta, tb, t32, t16, lp, tiles_m, stream);
-    case 4: return fp16 ? launch_cn<4, true>(ta, tb, t32, t16, lp, tiles_m, stream) : launch_cn<4, false>(ta, tb, t32, t16, lp, tiles_m, stream);
+    case 1: return fp16 ? launch_cn<1, true>(ta, tb, t16, lp, tiles_m, stream) : launch_cn<1, false>(ta, tb, t16, lp, tiles_m, stream);
+    case 2: return fp16 ? launch_cn<2, true>(ta, tb, t16, lp, tiles_m, stream) : launch_cn<2, false>(ta, tb, t16, lp, tiles_m, stream);
+    case 3: return fp16 ? launch_cn<3, true>(ta, tb, t16, lp, tiles_m, stream) : launch_cn<3, false>(ta, tb, t16, lp, tiles_m, stream);
+    case 4: return fp16 ? launch_cn<4, true>(ta, tb, t16, lp, tiles_m, stream) : launch_cn<4, false>(ta, tb, t16, lp, tiles_m, stream);
   }
   return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported hidden size");
 }
