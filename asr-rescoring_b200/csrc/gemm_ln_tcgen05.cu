@@ -45,8 +45,8 @@ constexpr int MAX_CN = 4;
 
 constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);       // 147456
 constexpr int SMEM_EPI = EPI_WARPS * 2 * BOX_BYTES;                        // 65536
-constexpr int SMEM_RED = 2 * 2 * BM * 4;                                   // sum / m2, two halves
-constexpr int SMEM_XCHG = 2 * MAX_CN * BM * 8;                             // [parity][rank][row] float2
+constexpr int SMEM_RED = 16;                                               // (unused)
+constexpr int SMEM_XCHG = 2 * 2 * MAX_CN * BM * 8;                         // [parity][rank*2+half][row] float2
 constexpr int SMEM_GB = 2 * BN * 4;                                        // gamma, beta slice
 constexpr int SMEM_BARS = 512;
 constexpr int SMEM_TOTAL = SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG + SMEM_GB + SMEM_BARS + 1024;
@@ -110,7 +110,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     if (++spins > (1u << 26)) __trap();
   }
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
@@ -131,6 +130,24 @@ __device__ __forceinline__ void tmem_ld_into(uint32_t taddr, uint32_t (&xr)[N]) 
       : "memory");
 }
 #undef PLLB_X
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 "
+      "[%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -165,7 +182,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sXchg = sRed + SMEM_RED;
   const uint32_t sGB = sXchg + SMEM_XCHG;
   const uint32_t sBar = sGB + SMEM_GB;
-  float* red = reinterpret_cast<float*>(smem_gen + SMEM_PIPE + SMEM_EPI);                 // [2 kinds][2 halves][128]
   float2* xchg = reinterpret_cast<float2*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED);   // [2][MAX_CN][128]
   float* gb = reinterpret_cast<float*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG);  // gamma[256], beta[256]
   const uint32_t bar_full = sBar;                         // STAGES
@@ -200,7 +216,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
         mbar_init(bar_tempty + 8 * s, EPI_WARPS);
-        mbar_init(bar_x + 8 * s, CN * BM);                 // every row-owner thread of every CTA arrives
+        mbar_init(bar_x + 8 * s, CN * 2 * BM);             // every epilogue thread of every CTA arrives
       }
       fence_barrier_init();
     }
@@ -265,138 +281,151 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 32-row block the 16-byte column groups of the 32 rows are contiguous, so thread
     // (row = lane) reading column group g touches base + ((blk * H/4 + g) * 32 + lane) * 16:
     // every warp access is one fully coalesced 512-byte segment, straight between global memory
-    // and the registers that mirror the TMEM layout (row per thread) — no shared-memory staging
-    // and no dependent TMA round trips for the residual in / fp32 out traffic.
+    // and registers in the TMEM layout (row per thread) — no staging for the residual in /
+    // fp32 out traffic.
+    //
+    // Pass A: x = acc + bias + residual, 16 columns at a time; shifted sums give this thread's
+    //         (mean, M2) over its 128 columns; x is parked back in TMEM (tcgen05.st) so that
+    //         only a chunk lives in registers.
+    // Exchange: every thread posts its (mean, M2) to all CTAs of the cluster (DSMEM) — 2*CN
+    //         groups of 128 columns per row — and the groups are merged with Chan's formula.
+    // Pass B: x back from TMEM, normalise, fp32 out (in place, coalesced), 16-bit copy through
+    //         two swizzled boxes + TMA.
     const int q = warp & 3;                    // TMEM lane quarter
     const int ew = warp - 2;
     const int half = ew >> 2;                  // which 128 columns of the tile
     const int cbase = half * EPI_COLS;
     const int row_in_tile = q * 32 + lane;
-    const uint32_t buf[2] = {sEpi + (ew * 2 + 0) * BOX_BYTES, sEpi + (ew * 2 + 1) * BOX_BYTES};
-    uint32_t acc = 0, acc_phase = 0, xpar = 0, xphase[2] = {0, 0};
-    const float inv_local = 1.0f / (float)BN, inv_h = 1.0f / (float)(CN * BN);
+    const uint32_t buf0 = sEpi + (ew * 2 + 0) * BOX_BYTES, buf1 = sEpi + (ew * 2 + 1) * BOX_BYTES;
+    uint32_t acc = 0, acc_phase = 0, xpar = 0, xphase0 = 0, xphase1 = 0;
+    constexpr int G = 2 * CN;                  // groups of 128 columns per row
     const int groups_per_row = p.H >> 2;
     const int g0 = (n0 + cbase) >> 2;          // first 4-column group of this thread
+    constexpr int NCH = EPI_COLS / 16;         // 8 chunks of 16 columns
 
     for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
       const int m0 = mb * BM;
       const int grow0 = m0 + q * 32;                         // first global row of this warp
       float4* hrow = reinterpret_cast<float4*>(p.hidden) + ((size_t)(grow0 >> 5) * groups_per_row + g0) * 32 + lane;
 
-      // residual slice (32 x float4 per thread): issued before the accumulator is ready, so the
-      // loads fly while the tensor core is still working on this tile
-      uint32_t xr[EPI_COLS];
+      // residual prefetch, two chunks deep (issued before the accumulator is ready)
+      float4 r0[4], r1[4];
 #pragma unroll
-      for (int i = 0; i < EPI_COLS / 4; ++i) {
-        const float4 v = hrow[(size_t)i * 32];
-        xr[4 * i + 0] = __float_as_uint(v.x); xr[4 * i + 1] = __float_as_uint(v.y);
-        xr[4 * i + 2] = __float_as_uint(v.z); xr[4 * i + 3] = __float_as_uint(v.w);
-      }
+      for (int i = 0; i < 4; ++i) { r0[i] = hrow[(size_t)i * 32]; r1[i] = hrow[(size_t)(4 + i) * 32]; }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tcgen05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
-      float sum = 0.f;
+
+      float pivot = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < EPI_COLS / 8; ++j) {
-        uint32_t t[8];
-        tmem_ld_x8(t_addr + 8 * j, t);
+      for (int j = 0; j < NCH; ++j) {
+        uint32_t t[16];
+        tmem_ld_x16(t_addr + 16 * j, t);
+        float4 rr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rr[i] = (j & 1) ? r1[i] : r0[i];
+        if (j + 2 < NCH) {                                  // refill the slot just consumed
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = hrow[(size_t)(4 * (j + 2) + i) * 32];
+            if (j & 1) r1[i] = v; else r0[i] = v;
+          }
+        }
         tcgen05_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float4 b = ldg_f4_ordered(p.bias + n0 + cbase + 8 * j + 4 * c);
-          const int i0 = 8 * j + 4 * c;
-          const float v0 = (__uint_as_float(t[4 * c + 0]) + b.x) + __uint_as_float(xr[i0 + 0]);
-          const float v1 = (__uint_as_float(t[4 * c + 1]) + b.y) + __uint_as_float(xr[i0 + 1]);
-          const float v2 = (__uint_as_float(t[4 * c + 2]) + b.z) + __uint_as_float(xr[i0 + 2]);
-          const float v3 = (__uint_as_float(t[4 * c + 3]) + b.w) + __uint_as_float(xr[i0 + 3]);
-          xr[i0 + 0] = __float_as_uint(v0); xr[i0 + 1] = __float_as_uint(v1);
-          xr[i0 + 2] = __float_as_uint(v2); xr[i0 + 3] = __float_as_uint(v3);
-          sum += (v0 + v1) + (v2 + v3);
+        for (int c = 0; c < 4; ++c) {
+          const float4 b = ldg_f4_ordered(p.bias + n0 + cbase + 16 * j + 4 * c);
+          const float v0 = (__uint_as_float(t[4 * c + 0]) + b.x) + rr[c].x;
+          const float v1 = (__uint_as_float(t[4 * c + 1]) + b.y) + rr[c].y;
+          const float v2 = (__uint_as_float(t[4 * c + 2]) + b.z) + rr[c].z;
+          const float v3 = (__uint_as_float(t[4 * c + 3]) + b.w) + rr[c].w;
+          if (j == 0 && c == 0) pivot = v0;                  // a sample of the row: no cancellation in s2
+          const float d0 = v0 - pivot, d1 = v1 - pivot, d2 = v2 - pivot, d3 = v3 - pivot;
+          s1 += (d0 + d1) + (d2 + d3);
+          s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+          t[4 * c + 0] = __float_as_uint(v0); t[4 * c + 1] = __float_as_uint(v1);
+          t[4 * c + 2] = __float_as_uint(v2); t[4 * c + 3] = __float_as_uint(v3);
+        }
+        tmem_st_x16(t_addr + 16 * j, t);
+      }
+      tcgen05_wait_st();
+      constexpr float inv_n = 1.0f / (float)EPI_COLS;
+      const float mean_t = pivot + s1 * inv_n;
+      const float m2_t = fmaxf(s2 - s1 * s1 * inv_n, 0.f);
+
+      // ---- exchange (mean, M2) of the 2*CN column groups of every row
+      {
+        const uint32_t slot = sXchg + (uint32_t)((xpar * (2 * MAX_CN) + rank * 2 + half) * BM + row_in_tile) * 8;
+        const uint32_t xb = bar_x + 8 * xpar;
+#pragma unroll
+        for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer) {
+          st_cluster_f32x2(mapa(slot, peer), mean_t, m2_t);
+          mbar_arrive_remote(mapa(xb, peer));
+        }
+        const uint32_t ph = xpar ? xphase1 : xphase0;
+        mbar_wait_cluster(xb, ph);
+        if (xpar) xphase1 ^= 1; else xphase0 ^= 1;
+      }
+      float mean = 0.f, M2 = 0.f;
+      {
+        float2 st[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          st[g] = xchg[(xpar * (2 * MAX_CN) + g) * BM + row_in_tile];
+          mean += st[g].x;
+        }
+        mean *= (1.0f / G);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float d = st[g].x - mean;
+          M2 += st[g].y + (float)EPI_COLS * d * d;           // Chan et al. merge of equal-size groups
         }
       }
-      // accumulator drained into registers: hand it back to the MMA warp
+      xpar ^= 1;
+      const float rstd = rsqrtf(M2 * (1.0f / (float)(G * EPI_COLS)) + p.eps);
+      const float nmr = -mean * rstd;
+
+      // ---- pass B
+      if (lane == 0) tma_store_wait_read<0>();               // previous tile's boxes left the staging buffers
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        uint32_t t[16];
+        tmem_ld_x16(t_addr + 16 * j, t);
+        tcgen05_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 g4 = lds_f4_ordered(sGB + (uint32_t)(cbase + 16 * j + 4 * c) * 4);
+          const float4 b4 = lds_f4_ordered(sGB + (uint32_t)(BN + cbase + 16 * j + 4 * c) * 4);
+          float4 y;
+          y.x = fmaf(fmaf(__uint_as_float(t[4 * c + 0]), rstd, nmr), g4.x, b4.x);
+          y.y = fmaf(fmaf(__uint_as_float(t[4 * c + 1]), rstd, nmr), g4.y, b4.y);
+          y.z = fmaf(fmaf(__uint_as_float(t[4 * c + 2]), rstd, nmr), g4.z, b4.z);
+          y.w = fmaf(fmaf(__uint_as_float(t[4 * c + 3]), rstd, nmr), g4.w, b4.w);
+          hrow[(size_t)(4 * j + c) * 32] = y;
+          pk[2 * c + 0] = pack16x2<FP16>(y.x, y.y);
+          pk[2 * c + 1] = pack16x2<FP16>(y.z, y.w);
+        }
+        // 16 columns = 32 bytes = chunks 2*(j&3), 2*(j&3)+1 of box (j >> 2)
+        const uint32_t bx = (j >> 2) ? buf1 : buf0;
+        const int c16 = 2 * (j & 3);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bx + lane * 128 + (((c16) ^ (lane & 7)) << 4)),
+                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bx + lane * 128 + (((c16 + 1) ^ (lane & 7)) << 4)),
+                     "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      }
+      // accumulator columns are free again
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-
-      // ---- per-row statistics: local mean, local M2, then merge across the cluster
-      red[half * BM + row_in_tile] = sum;
-      epi_bar_sync();
-      const float mean_loc = (red[row_in_tile] + red[BM + row_in_tile]) * inv_local;
-      float m2 = 0.f;
-#pragma unroll
-      for (int i = 0; i < EPI_COLS; ++i) {
-        const float d = __uint_as_float(xr[i]) - mean_loc;
-        m2 = fmaf(d, d, m2);
-      }
-      red[2 * BM + half * BM + row_in_tile] = m2;
-      epi_bar_sync();
-      float mean = mean_loc;
-      float M2 = red[2 * BM + row_in_tile] + red[3 * BM + row_in_tile];
-      if constexpr (CN > 1) {
-        if (half == 0) {
-          const uint32_t slot = sXchg + (uint32_t)((xpar * MAX_CN + rank) * BM + row_in_tile) * 8;
-#pragma unroll
-          for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer) {
-            st_cluster_f32x2(mapa(slot, peer), mean_loc, M2);
-            mbar_arrive_remote(mapa(bar_x + 8 * xpar, peer));
-          }
-        }
-        mbar_wait_cluster(bar_x + 8 * xpar, xphase[xpar]);
-        xphase[xpar] ^= 1;
-        float msum = 0.f;
-        float2 st[CN];
-#pragma unroll
-        for (int r2 = 0; r2 < CN; ++r2) {
-          st[r2] = xchg[(xpar * MAX_CN + r2) * BM + row_in_tile];
-          msum += st[r2].x;
-        }
-        mean = msum * (1.0f / CN);
-        M2 = 0.f;
-#pragma unroll
-        for (int r2 = 0; r2 < CN; ++r2) {
-          const float d = st[r2].x - mean;
-          M2 += st[r2].y + (float)BN * d * d;                // Chan et al. pairwise merge
-        }
-        xpar ^= 1;
-      }
-      const float rstd = rsqrtf(M2 * inv_h + p.eps);
-
-      // ---- normalise in registers; fp32 goes straight back (coalesced, in place), the 16-bit
-      //      operand copy is row-major for the next GEMM's TMA: two swizzled boxes + TMA stores
-      if (lane == 0) tma_store_wait_read<0>();               // previous tile's boxes left the staging buffers
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < EPI_COLS / 4; ++i) {
-        const float4 g4 = lds_f4_ordered(sGB + (uint32_t)(cbase + 4 * i) * 4);
-        const float4 b4 = lds_f4_ordered(sGB + (uint32_t)(BN + cbase + 4 * i) * 4);
-        float4 y;
-        y.x = fmaf((__uint_as_float(xr[4 * i + 0]) - mean) * rstd, g4.x, b4.x);
-        y.y = fmaf((__uint_as_float(xr[4 * i + 1]) - mean) * rstd, g4.y, b4.y);
-        y.z = fmaf((__uint_as_float(xr[4 * i + 2]) - mean) * rstd, g4.z, b4.z);
-        y.w = fmaf((__uint_as_float(xr[4 * i + 3]) - mean) * rstd, g4.w, b4.w);
-        hrow[(size_t)i * 32] = y;
-        xr[2 * i + 0] = pack16x2<FP16>(y.x, y.y);            // compact in place: 2 packed words per group
-        xr[2 * i + 1] = pack16x2<FP16>(y.z, y.w);
-      }
-#pragma unroll
-      for (int bx = 0; bx < 2; ++bx) {                       // box bx: columns cbase + 64*bx .. +63
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int w0 = 32 * bx + 4 * c;
-          const uint32_t dst = buf[bx] + lane * 128 + ((c ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(xr[w0 + 0]), "r"(xr[w0 + 1]),
-                       "r"(xr[w0 + 2]), "r"(xr[w0 + 3])
-                       : "memory");
-        }
-      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&tmH16, buf[0], n0 + cbase, grow0);
-        tma_store_2d(&tmH16, buf[1], n0 + cbase + 64, grow0);
+        tma_store_2d(&tmH16, buf0, n0 + cbase, grow0);
+        tma_store_2d(&tmH16, buf1, n0 + cbase + 64, grow0);
         tma_store_commit();
       }
     }
