@@ -47,9 +47,11 @@ constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);       // 147
 constexpr int SMEM_EPI = EPI_WARPS * 2 * BOX_BYTES;                        // 65536
 constexpr int SMEM_RED = 16;                                               // (unused)
 constexpr int SMEM_XCHG = 2 * 2 * MAX_CN * BM * 8;                         // [parity][rank*2+half][row] float2
-constexpr int SMEM_GB = 2 * BN * 4;                                        // gamma, beta slice
+constexpr int SMEM_GB = 0;                                                 // gamma / beta come through the read-only L1 path
 constexpr int SMEM_BARS = 512;
 constexpr int SMEM_TOTAL = SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG + SMEM_GB + SMEM_BARS + 1024;
+
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget of one CTA");
 
 struct LnParams {
   int M, K, H;
@@ -183,7 +185,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sGB = sXchg + SMEM_XCHG;
   const uint32_t sBar = sGB + SMEM_GB;
   float2* xchg = reinterpret_cast<float2*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED);   // [2][MAX_CN][128]
-  float* gb = reinterpret_cast<float*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG);  // gamma[256], beta[256]
   const uint32_t bar_full = sBar;                         // STAGES
   const uint32_t bar_empty = bar_full + 8 * STAGES;       // STAGES
   const uint32_t bar_tfull = bar_empty + 8 * STAGES;      // 2
@@ -223,11 +224,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
-  }
-  // gamma / beta slice of this CTA's 256 columns
-  for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {
-    gb[i] = p.gamma[n0 + i];
-    gb[BN + i] = p.beta[n0 + i];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -396,8 +392,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t pk[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 g4 = lds_f4_ordered(sGB + (uint32_t)(cbase + 16 * j + 4 * c) * 4);
-          const float4 b4 = lds_f4_ordered(sGB + (uint32_t)(BN + cbase + 16 * j + 4 * c) * 4);
+          const float4 g4 = ldg_f4_ordered(p.gamma + n0 + cbase + 16 * j + 4 * c);
+          const float4 b4 = ldg_f4_ordered(p.beta + n0 + cbase + 16 * j + 4 * c);
           float4 y;
           y.x = fmaf(fmaf(__uint_as_float(t[4 * c + 0]), rstd, nmr), g4.x, b4.x);
           y.y = fmaf(fmaf(__uint_as_float(t[4 * c + 1]), rstd, nmr), g4.y, b4.y);
