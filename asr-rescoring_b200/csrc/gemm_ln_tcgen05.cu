@@ -93,8 +93,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+// DSMEM message: 8-byte store into a peer CTA's shared memory that completes 8 tx bytes on the
+// peer's mbarrier (SASS STAS) — no fences, no release/acquire round trips.
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -217,7 +220,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
         mbar_init(bar_tempty + 8 * s, EPI_WARPS);
-        mbar_init(bar_x + 8 * s, CN * 2 * BM);             // every epilogue thread of every CTA arrives
+        mbar_init(bar_x + 8 * s, 1);                       // armed once per tile with the expected byte count
       }
       fence_barrier_init();
     }
@@ -304,10 +307,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int grow0 = m0 + q * 32;                         // first global row of this warp
       float4* hrow = reinterpret_cast<float4*>(p.hidden) + ((size_t)(grow0 >> 5) * groups_per_row + g0) * 32 + lane;
 
-      // residual prefetch, two chunks deep (issued before the accumulator is ready)
-      float4 r0[4], r1[4];
+      // residual prefetch, four 16-column chunks deep (issued before the accumulator is ready)
+      float4 rs[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { r0[i] = hrow[(size_t)i * 32]; r1[i] = hrow[(size_t)(4 + i) * 32]; }
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rs[k][i] = hrow[(size_t)(4 * k + i) * 32];
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tcgen05_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
@@ -319,13 +324,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_x16(t_addr + 16 * j, t);
         float4 rr[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rr[i] = (j & 1) ? r1[i] : r0[i];
-        if (j + 2 < NCH) {                                  // refill the slot just consumed
+        for (int i = 0; i < 4; ++i) rr[i] = rs[j & 3][i];
+        if (j + 4 < NCH) {                                  // refill the slot just consumed
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 v = hrow[(size_t)(4 * (j + 2) + i) * 32];
-            if (j & 1) r1[i] = v; else r0[i] = v;
-          }
+          for (int i = 0; i < 4; ++i) rs[j & 3][i] = hrow[(size_t)(4 * (j + 4) + i) * 32];
         }
         tcgen05_wait_ld();
 #pragma unroll
@@ -353,13 +355,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       {
         const uint32_t slot = sXchg + (uint32_t)((xpar * (2 * MAX_CN) + rank * 2 + half) * BM + row_in_tile) * 8;
         const uint32_t xb = bar_x + 8 * xpar;
+        if (ew == 0 && lane == 0) mbar_arrive_expect_tx(xb, CN * EPI_WARPS * 32 * 8);   // this tile's inbox
 #pragma unroll
-        for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer) {
-          st_cluster_f32x2(mapa(slot, peer), mean_t, m2_t);
-          mbar_arrive_remote(mapa(xb, peer));
-        }
+        for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer)
+          st_async_f32x2(mapa(slot, peer), mean_t, m2_t, mapa(xb, peer));
         const uint32_t ph = xpar ? xphase1 : xphase0;
-        mbar_wait_cluster(xb, ph);
+        mbar_wait(xb, ph);
         if (xpar) xphase1 ^= 1; else xphase0 ^= 1;
       }
       float mean = 0.f, M2 = 0.f;
