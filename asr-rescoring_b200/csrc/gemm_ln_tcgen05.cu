@@ -32,7 +32,10 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+// STAGED = true : 3-stage operand ring + the 16-bit output through two swizzled boxes per warp and TMA
+//                 stores (best when the epilogue paces the kernel: K = H, attention output);
+// STAGED = false: 4-stage operand ring, 16-bit output written straight from registers (best when
+//                 the mainloop paces the kernel: K = 4H, FFN2).
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -43,15 +46,17 @@ constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_CN = 4;
 
-constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);       // 147456
-constexpr int SMEM_EPI = 0;                                                // the epilogue needs no staging
 constexpr int SMEM_RED = 16;                                               // (unused)
 constexpr int SMEM_XCHG = 2 * 2 * MAX_CN * BM * 8;                         // [parity][rank*2+half][row] float2
 constexpr int SMEM_GB = 0;                                                 // gamma / beta come through the read-only L1 path
 constexpr int SMEM_BARS = 512;
-constexpr int SMEM_TOTAL = SMEM_PIPE + SMEM_EPI + SMEM_RED + SMEM_XCHG + SMEM_GB + SMEM_BARS + 1024;
+template <bool STAGED>
+constexpr int smem_total() {
+  return (STAGED ? 3 : 4) * (A_STAGE_BYTES + B_STAGE_BYTES) + (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + SMEM_RED +
+         SMEM_XCHG + SMEM_GB + SMEM_BARS + 1024;
+}
 
-static_assert(SMEM_TOTAL <= 232448, "shared memory budget of one CTA");
+static_assert(smem_total<true>() <= 232448 && smem_total<false>() <= 232448, "shared memory budget of one CTA");
 
 struct LnParams {
   int M, K, H;
@@ -173,10 +178,13 @@ __device__ __forceinline__ float4 lds_f4_ordered(uint32_t addr) {
   return v;
 }
 
-template <int CN, bool FP16>
+template <int CN, bool FP16, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const LnParams p) {
+               const __grid_constant__ CUtensorMap tmH16, const LnParams p) {
+  constexpr int STAGES = STAGED ? 3 : 4;
+  constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  constexpr int SMEM_EPI = STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
@@ -295,6 +303,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;                  // which 128 columns of the tile
     const int cbase = half * EPI_COLS;
     const int row_in_tile = q * 32 + lane;
+    const uint32_t buf0 = sEpi + (ew * 2 + 0) * BOX_BYTES, buf1 = sEpi + (ew * 2 + 1) * BOX_BYTES;   // STAGED only
     uint32_t acc = 0, acc_phase = 0, xpar = 0, xphase0 = 0, xphase1 = 0;
     constexpr int G = 2 * CN;                  // groups of 128 columns per row
     const int groups_per_row = p.H >> 2;
@@ -386,6 +395,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       //      bytes of its row and writes them 32 bytes per chunk.
       uint4* orow = reinterpret_cast<uint4*>(p.hidden16 + (size_t)(grow0 + lane) * p.H + n0 + cbase);
       const bool row_ok = grow0 + lane < p.M;
+      if constexpr (STAGED) {
+        if (lane == 0) tma_store_wait_read<0>();             // previous tile's boxes left the staging buffers
+        __syncwarp();
+      }
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         uint32_t t[16];
@@ -405,7 +418,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           pk[2 * c + 0] = pack16x2<FP16>(y.x, y.y);
           pk[2 * c + 1] = pack16x2<FP16>(y.z, y.w);
         }
-        if (row_ok) {
+        if constexpr (STAGED) {
+          // 16 columns = 32 bytes = chunks 2*(j&3), 2*(j&3)+1 of box (j >> 2)
+          const uint32_t bx = (j >> 2) ? buf1 : buf0;
+          const int c16 = 2 * (j & 3);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bx + lane * 128 + (((c16) ^ (lane & 7)) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bx + lane * 128 + (((c16 + 1) ^ (lane & 7)) << 4)),
+                       "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        } else if (row_ok) {
           orow[2 * j + 0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           orow[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
@@ -416,6 +437,18 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if constexpr (STAGED) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmH16, buf0, n0 + cbase, grow0);
+          tma_store_2d(&tmH16, buf1, n0 + cbase + 64, grow0);
+          tma_store_commit();
+        }
+      }
+    }
+    if constexpr (STAGED) {
+      if (lane == 0) tma_store_wait_all();
     }
   }
 
@@ -459,10 +492,11 @@ int tmap2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt, ui
   return PLLB_OK;
 }
 
-template <int CN, bool FP16>
-int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb,
+template <int CN, bool FP16, bool STAGED>
+int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t16,
               const LnParams& lp, int64_t tiles_m, cudaStream_t stream) {
-  auto kern = gemm_ln_kernel<CN, FP16>;
+  auto kern = gemm_ln_kernel<CN, FP16, STAGED>;
+  constexpr int SMEM_TOTAL = smem_total<STAGED>();
   PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(NUM_THREADS);
@@ -476,8 +510,8 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent: as many clusters as can be co-resident (clusters must fit inside a GPC)
-  static thread_local int max_clusters[MAX_CN + 1][2] = {};
-  int& mc = max_clusters[CN][FP16 ? 1 : 0];
+  static thread_local int max_clusters[MAX_CN + 1][4] = {};
+  int& mc = max_clusters[CN][(FP16 ? 1 : 0) + (STAGED ? 2 : 0)];
   if (mc == 0) {
     cfg.gridDim = dim3(CN * (sm_count() / CN));
     int n = 0;
@@ -490,7 +524,7 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb,
   }
   const int clusters = (int)(tiles_m < mc ? tiles_m : mc);
   cfg.gridDim = dim3(CN * clusters);
-  PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, lp));
+  PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t16, lp));
   ++g_launch_counter;
   return PLLB_OK;
 }
@@ -502,18 +536,28 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   if (M <= 0) return PLLB_OK;
   if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, t16;
   int rc;
   if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
   if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, BN, BK))) return rc;
+  if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
   LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps};
   const int64_t tiles_m = ceil_div(M, BM);
+  // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
+  const bool staged = K <= H;
+#define PLLB_LN(CN_)                                                                                          \
+  case CN_:                                                                                                   \
+    if (fp16) return staged ? launch_cn<CN_, true, true>(ta, tb, t16, lp, tiles_m, stream)                    \
+                            : launch_cn<CN_, true, false>(ta, tb, t16, lp, tiles_m, stream);                  \
+    return staged ? launch_cn<CN_, false, true>(ta, tb, t16, lp, tiles_m, stream)                             \
+                  : launch_cn<CN_, false, false>(ta, tb, t16, lp, tiles_m, stream);
   switch (H / BN) {
-    case 1: return fp16 ? launch_cn<1, true>(ta, tb, lp, tiles_m, stream) : launch_cn<1, false>(ta, tb, lp, tiles_m, stream);
-    case 2: return fp16 ? launch_cn<2, true>(ta, tb, lp, tiles_m, stream) : launch_cn<2, false>(ta, tb, lp, tiles_m, stream);
-    case 3: return fp16 ? launch_cn<3, true>(ta, tb, lp, tiles_m, stream) : launch_cn<3, false>(ta, tb, lp, tiles_m, stream);
-    case 4: return fp16 ? launch_cn<4, true>(ta, tb, lp, tiles_m, stream) : launch_cn<4, false>(ta, tb, lp, tiles_m, stream);
+    PLLB_LN(1)
+    PLLB_LN(2)
+    PLLB_LN(3)
+    PLLB_LN(4)
   }
+#undef PLLB_LN
   return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported hidden size");
 }
 
