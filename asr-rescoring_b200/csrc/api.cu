@@ -187,7 +187,8 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   const int H = d.hidden, I = d.intermediate;
   RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, c->plan, s));
   RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
-                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->hidden_f32, c->hidden_bf16, c->fp16, s));
+                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->y_f32, c->hidden_bf16, c->fp16, s));
+  RC(launch_rowmajor_to_t32(c->y_f32, c->hidden_f32, n_rows, H, s));
   const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
   // Only the [MASK] row of each copy reaches the MLM head (MLM_PLL/main.py:101), and after the
   // last layer's attention every remaining op is row-wise: the last layer's output

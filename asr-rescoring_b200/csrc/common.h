@@ -93,7 +93,7 @@ int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPla
 int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                     const float* word_emb, const float* pos_emb, const float* type_emb, const float* g,
                     const float* b, float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id,
-                    float* hidden_f32, void* hidden_bf16, bool fp16, cudaStream_t s);
+                    float* hidden_f32_rowmajor, void* hidden_bf16, bool fp16, cudaStream_t s);
 // hidden = LN(y + hidden) (in place), hidden_bf16 = bf16(hidden)
 int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b,
                        float eps, int64_t rows, int H, bool fp16, cudaStream_t s);
@@ -112,6 +112,7 @@ int launch_lse_finish(const float2* partials, const float* label_logit, int32_t 
 int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,
                    float* out_tok_logp, cudaStream_t s);
 // T32 blocked fp32 [rows, H] -> row-major fp32 (debug / parity output)
+int launch_rowmajor_to_t32(const float* src, float* dst, int64_t rows, int H, cudaStream_t s);
 int launch_t32_to_rowmajor(const float* src, float* dst, int64_t rows, int H, cudaStream_t s);
 int launch_f32_to_bf16(const float* src, void* dst, int64_t n, bool fp16, cudaStream_t s);
 

@@ -174,7 +174,11 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
     }
     ln_normalize<VEC>(x, g, b, eps, lane);
     const size_t row = (size_t)(start + p);
-    store_row<VEC, FP16>(x, t32_row<VEC>(hidden_f32, (int64_t)row), hidden_bf16 + row * H, lane);
+    // fp32 goes out row-major here (one coalesced 3 KB row per warp); rowmajor_to_t32_kernel
+    // re-tiles it into the T32 residual layout with fully coalesced accesses on both sides.
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) reinterpret_cast<float4*>(hidden_f32 + row * H)[lane + 32 * i] = x[i];
+    store_row<VEC, FP16>(x, nullptr, hidden_bf16 + row * H, lane);
   }
 }
 
@@ -605,6 +609,30 @@ __global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int3
   for (int i = lane; i < G; i += 32) d[(size_t)i * 32] = s[(size_t)i * 32];
 }
 
+// row-major fp32 [rows, H] -> T32 blocked layout; one CTA per (32-row block, 128-column slab)
+__global__ void __launch_bounds__(256)
+rowmajor_to_t32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int H) {
+  __shared__ float tile[32][132];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 128;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                               // warp w loads rows w, w+8, w+16, w+24 (512 B each)
+    const int r = w + 8 * k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < rows) v = *reinterpret_cast<const float4*>(src + (r0 + r) * H + c0 + 4 * lane);
+    *reinterpret_cast<float4*>(&tile[r][4 * lane]) = v;
+  }
+  __syncthreads();
+  const int G = H / 4;
+  float4* out = reinterpret_cast<float4*>(dst) + ((size_t)blockIdx.x * G + c0 / 4) * 32 + lane;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {                               // warp w writes column groups w, w+8, ... (512 B each)
+    const int g = w + 8 * k;
+    out[(size_t)g * 32] = *reinterpret_cast<const float4*>(&tile[lane][4 * g]);
+  }
+}
+
 __global__ void t32_to_rowmajor_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int H) {
   const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -808,6 +836,15 @@ int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t 
   if (n_hyp <= 0) return PLLB_OK;
   hyp_sum_kernel<<<(unsigned)ceil_div(n_hyp, 128), 128, 0, s>>>(tok_logp, hyp_copy_base, n_hyp, out_pll, out_tok_logp);
   PLLB_LAUNCH_CHECK("hyp_sum_kernel");
+  return PLLB_OK;
+}
+
+int launch_rowmajor_to_t32(const float* src, float* dst, int64_t rows, int H, cudaStream_t s) {
+  if (rows <= 0) return PLLB_OK;
+  if (H % 128 != 0) return fail(PLLB_ERR_INVALID, "rowmajor_to_t32: H % 128 != 0");
+  dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)(H / 128));
+  rowmajor_to_t32_kernel<<<grid, 256, 0, s>>>(src, dst, rows, H);
+  PLLB_LAUNCH_CHECK("rowmajor_to_t32_kernel");
   return PLLB_OK;
 }
 
