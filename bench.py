@@ -362,10 +362,15 @@ def main():
                                    "sample": f"first {min(args.cpu_sample_hyps, n_hyp)} hypotheses ({copies} masked copies) "
                                              f"of the same workload, oracle port of MLM_PLL/main.py run_one_epoch, "
                                              f"batch 32, fp32, {dt:.1f} s"}
-        print(json.dumps(out))
+    else:
+        out = None
     scorer.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if out is not None:
+        sys.stderr.flush()
+        print(json.dumps(out), flush=True)     # the JSON line is the last thing rank 0 prints
 
 
 if __name__ == "__main__":
