@@ -185,9 +185,9 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
               float* out_tok_logp, int upto_layer, cudaStream_t s) {
   const pllb_model_desc& d = c->d;
   const int H = d.hidden, I = d.intermediate;
-  RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, c->plan, s));
+  RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, d.vocab, c->plan, s));
   RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
-                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, c->y_f32, c->hidden_bf16, c->fp16, s));
+                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->hidden_bf16, c->fp16, s));
   RC(launch_rowmajor_to_t32(c->y_f32, c->hidden_f32, n_rows, H, s));
   const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
   // Only the [MASK] row of each copy reaches the MLM head (MLM_PLL/main.py:101), and after the
@@ -534,6 +534,12 @@ int pllb_score_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off
   if (!off || !out_pll) return fail(PLLB_ERR_INVALID, "pllb_score_host: null argument");
   PLLB_CUDA(cudaSetDevice(h->device));
   const int64_t n_tok = off[n_hyp] - off[0];
+  if (n_tok > 0 && !hyp_tokens) return fail(PLLB_ERR_INVALID, "pllb_score_host: hyp_tokens is null");
+  // the reference's embedding lookup raises IndexError on an id outside the vocabulary
+  for (int64_t i = off[0]; i < off[n_hyp]; ++i)
+    if (hyp_tokens[i] < 0 || hyp_tokens[i] >= h->d.vocab)
+      return fail(PLLB_ERR_INVALID, "token id " + std::to_string(hyp_tokens[i]) + " at position " + std::to_string(i) +
+                                        " is outside the vocabulary [0, " + std::to_string(h->d.vocab) + ")");
   const int64_t b_tok = align_up(sizeof(int32_t) * std::max<int64_t>(n_tok, 1), 256);
   const int64_t b_pll = align_up(sizeof(double) * n_hyp, 256);
   const int64_t b_lp = align_up(sizeof(float) * std::max<int64_t>(n_tok, 1), 256);
@@ -579,7 +585,8 @@ int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, in
   PLLB_CUDA(cudaMemcpyAsync(h->meta_dev, h->meta_host, sizeof(int32_t) * 3 * (n_hyp + 1), cudaMemcpyHostToDevice, s));
   const int32_t* d_tok_off = h->meta_dev;
   hyp_tokens += off[0];
-  RC(launch_expand_plan(hyp_tokens, d_tok_off, d_tok_off + (n_hyp + 1), d_tok_off + 2 * (n_hyp + 1), n_hyp, h->plan, s));
+  RC(launch_expand_plan(hyp_tokens, d_tok_off, d_tok_off + (n_hyp + 1), d_tok_off + 2 * (n_hyp + 1), n_hyp, h->d.vocab,
+                        h->plan, s));
   RC(launch_expand_ids(hyp_tokens, d_tok_off, h->plan, (int32_t)copies, h->d.cls_id, h->d.sep_id, h->d.mask_id, out_ids,
                        out_mask_pos, out_labels, s));
   return PLLB_OK;

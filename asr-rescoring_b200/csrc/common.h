@@ -86,13 +86,13 @@ struct CopyPlan {          // device arrays, one entry per masked copy of the ch
 };
 
 int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
-                       const int32_t* hyp_row_base, int32_t n_hyp, CopyPlan plan, cudaStream_t s);
+                       const int32_t* hyp_row_base, int32_t n_hyp, int32_t vocab, CopyPlan plan, cudaStream_t s);
 int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                       int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t* out_ids, int32_t* out_mask_pos,
                       int32_t* out_labels, cudaStream_t s);
 int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                     const float* word_emb, const float* pos_emb, const float* type_emb, const float* g,
-                    const float* b, float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id,
+                    const float* b, float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t vocab,
                     float* hidden_f32_rowmajor, void* hidden_bf16, bool fp16, cudaStream_t s);
 // hidden = LN(y + hidden) (in place), hidden_bf16 = bf16(hidden)
 int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b,

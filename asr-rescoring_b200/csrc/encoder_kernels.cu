@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
 // One thread per hypothesis: writes the descriptors of its L masked copies.
 __global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off,
                                    const int32_t* __restrict__ hyp_copy_base, const int32_t* __restrict__ hyp_row_base,
-                                   int32_t n_hyp, CopyPlan plan) {
+                                   int32_t n_hyp, int32_t vocab, CopyPlan plan) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_hyp) return;
   const int t0 = hyp_tok_off[h];
@@ -59,7 +59,7 @@ __global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int
     plan.seq_start[c] = r0 + m * T;
     plan.seq_len[c] = T;
     plan.mask_row[c] = r0 + m * T + m + 1;
-    plan.label[c] = tokens[t0 + m];
+    plan.label[c] = min(max(tokens[t0 + m], 0), vocab - 1);   // ids are validated on the host; clamp = memory safety
     plan.hyp[c] = h;
   }
 }
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off, CopyPlan plan,
                 int32_t n_copies, const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
                 const float* __restrict__ type_emb, const float* __restrict__ g, const float* __restrict__ b, float eps,
-                int cls_id, int sep_id, int mask_id, float* __restrict__ hidden_f32,
+                int cls_id, int sep_id, int mask_id, int vocab, float* __restrict__ hidden_f32,
                 __nv_bfloat16* __restrict__ hidden_bf16) {
   constexpr int H = 128 * VEC;
   const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -160,7 +160,7 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
   const int m = plan.mask_row[c] - start - 1;
   const int t0 = hyp_tok_off[plan.hyp[c]];
   for (int p = 0; p < T; ++p) {
-    const int id = copy_token_id(tokens, t0, T, m, p, cls_id, sep_id, mask_id);
+    const int id = min(max(copy_token_id(tokens, t0, T, m, p, cls_id, sep_id, mask_id), 0), vocab - 1);
     const float4* w = reinterpret_cast<const float4*>(word_emb + (size_t)id * H);
     const float4* pe = reinterpret_cast<const float4*>(pos_emb + (size_t)p * H);
     const float4* te = reinterpret_cast<const float4*>(type_emb);
@@ -698,10 +698,10 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 
 // ------------------------------------------------------------------ launchers
 int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
-                       const int32_t* hyp_row_base, int32_t n_hyp, CopyPlan plan, cudaStream_t s) {
+                       const int32_t* hyp_row_base, int32_t n_hyp, int32_t vocab, CopyPlan plan, cudaStream_t s) {
   if (n_hyp <= 0) return PLLB_OK;
   expand_plan_kernel<<<(unsigned)ceil_div(n_hyp, 128), 128, 0, s>>>(tokens, hyp_tok_off, hyp_copy_base, hyp_row_base,
-                                                                   n_hyp, plan);
+                                                                   n_hyp, vocab, plan);
   PLLB_LAUNCH_CHECK("expand_plan_kernel");
   return PLLB_OK;
 }
@@ -727,12 +727,13 @@ int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPla
 
 int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                     const float* word_emb, const float* pos_emb, const float* type_emb, const float* g, const float* b,
-                    float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id, float* hidden_f32,
+                    float eps, int H, int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t vocab, float* hidden_f32,
                     void* hidden_bf16, bool fp16, cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   const unsigned grid = (unsigned)ceil_div(n_copies, WARPS_PER_BLOCK);
 #define EMB(F) embed_ln_kernel<VEC, F><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(                                         \
-      tokens, hyp_tok_off, plan, n_copies, word_emb, pos_emb, type_emb, g, b, eps, cls_id, sep_id, mask_id, hidden_f32, \
+      tokens, hyp_tok_off, plan, n_copies, word_emb, pos_emb, type_emb, g, b, eps, cls_id, sep_id, mask_id, vocab,       \
+      hidden_f32,                                                                                                      \
       reinterpret_cast<__nv_bfloat16*>(hidden_bf16))
   PLLB_DISPATCH_VEC(H, (fp16 ? EMB(true) : EMB(false)));
 #undef EMB

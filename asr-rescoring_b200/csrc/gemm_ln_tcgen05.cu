@@ -79,11 +79,6 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
   }
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ uint32_t cluster_id_x() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
@@ -120,9 +115,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     if (ok) break;
     if (++spins > (1u << 26)) __trap();
   }
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
 
 // tcgen05.ld 32 lanes x 32 columns straight into x[OFF .. OFF+31] (no staging registers)

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -108,7 +109,10 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
   }
 }
 
-template <int EPI, bool FP16>
+// MC: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (same
+// weight columns): each CTA fetches half of the 256x64 W box and TMA-multicasts it to both,
+// which halves the L2 -> SM weight traffic; the stage-release barrier then counts both CTAs.
+template <int EPI, bool FP16, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
@@ -129,8 +133,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int tiles_n = p.N / BN;
   const int tiles_m = (p.M + BM - 1) / BM;
-  const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BK;
+  // work units: one tile per CTA, or (MC) a pair of vertically adjacent tiles per cluster
+  const uint32_t crank = MC ? cluster_ctarank() : 0;
+  const int unit0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = (MC ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+#define PLLB_TILE_M(tile) ((MC ? 2 * ((tile) / tiles_n) + (int)crank : (tile) / tiles_n) * BM)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -141,7 +150,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(bar_full + 8 * s, 1);
-        mbar_init(bar_empty + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, MC ? 2 : 1);           // MC: both CTAs' MMAs must have retired
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
@@ -155,6 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -162,13 +172,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM;
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+        const int m0 = PLLB_TILE_M(tile);
         const int n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
           tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m0);
+          if constexpr (MC) {
+            // my half of the W box (128 rows = 16 KiB), delivered to both CTAs
+            tma_load_2d_multicast(sB + stage * B_STAGE_BYTES + crank * (B_STAGE_BYTES / 2), &tmB, bar_full + 8 * stage,
+                                  kb * BK, n0 + (int)crank * (BN / 2), (uint16_t)0x3);
+          } else
           tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -179,7 +194,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc = FP16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -194,7 +209,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2);
             tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(bar_empty + 8 * stage);          // smem stage reusable once MMAs retire
+          if constexpr (MC) tcgen05_commit_multicast(bar_empty + 8 * stage, (uint16_t)0x3);
+          else tcgen05_commit(bar_empty + 8 * stage);     // smem stage reusable once MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(bar_tfull + 8 * acc);              // accumulator complete
@@ -209,8 +225,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cbase = (ew >> 2) * EPI_COLS;               // first tile column owned by this warp
     const uint32_t my_buf = sEpi + ew * EPI_BUFS * EPI_BUF_BYTES;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM;
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      const int m0 = PLLB_TILE_M(tile);
       const int tn = tile % tiles_n;
       const int n0 = tn * BN;
       const int row = m0 + q * 32 + lane;
@@ -335,10 +351,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();       // the peer may still multicast-arrive on this CTA's barriers
   if (warp == 1) {
+    __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+#undef PLLB_TILE_M
 }
 
 // ------------------------------------------------------------------ host side
@@ -375,18 +394,49 @@ int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_
   return PLLB_OK;
 }
 
-template <int EPI, bool FP16>
-int launch_epi2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
+template <int EPI, bool FP16, bool MC>
+int launch_epi3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
                 cudaStream_t stream) {
-  PLLB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<EPI, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-  gemm_tcgen05_kernel<EPI, FP16><<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(a, b, c, kp);
-  PLLB_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  auto kern = gemm_tcgen05_kernel<EPI, FP16, MC>;
+  PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  if constexpr (MC) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, a, b, c, kp));
+    ++g_launch_counter;
+  } else {
+    kern<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(a, b, c, kp);
+    PLLB_LAUNCH_CHECK("gemm_tcgen05_kernel");
+  }
   return PLLB_OK;
 }
 template <int EPI>
 int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid, bool fp16,
-               cudaStream_t stream) {
-  return fp16 ? launch_epi2<EPI, true>(a, b, c, kp, grid, stream) : launch_epi2<EPI, false>(a, b, c, kp, grid, stream);
+               bool mc, cudaStream_t stream) {
+  if (mc)
+    return fp16 ? launch_epi3<EPI, true, true>(a, b, c, kp, grid, stream)
+                : launch_epi3<EPI, false, true>(a, b, c, kp, grid, stream);
+  return fp16 ? launch_epi3<EPI, true, false>(a, b, c, kp, grid, stream)
+              : launch_epi3<EPI, false, false>(a, b, c, kp, grid, stream);
+}
+
+bool multicast_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PLLB_GEMM_MULTICAST");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
 }
 
 }  // namespace
@@ -399,7 +449,8 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
-  if ((rc = make_tmap(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, BN, BK))) return rc;
+  const bool mc = multicast_enabled() && M > BM;         // pairs of vertically adjacent tiles share W
+  if ((rc = make_tmap(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, mc ? BN / 2 : BN, BK))) return rc;
   tc = ta;
   if (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16) {
     if ((rc = make_tmap(&tc, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)N, 32, 64))) return rc;
@@ -412,14 +463,21 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
     if (!lse) return fail(PLLB_ERR_INVALID, "gemm: LSE epilogue needs LseArgs");
     kp.lse = *lse;
   }
-  const int64_t tiles = ceil_div(M, BM) * (N / BN);
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  int grid;
+  if (mc) {
+    const int64_t units = ceil_div(ceil_div(M, BM), 2) * (N / BN);
+    const int64_t clusters = units < sm_count() / 2 ? units : sm_count() / 2;
+    grid = (int)(2 * clusters);
+  } else {
+    const int64_t tiles = ceil_div(M, BM) * (N / BN);
+    grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  }
   switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, fp16, stream);
-    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, fp16, stream);
-    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, fp16, stream);
-    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, fp16, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, fp16, stream);
+    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, fp16, mc, stream);
+    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, fp16, mc, stream);
+    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, fp16, mc, stream);
+    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, fp16, mc, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, fp16, mc, stream);
   }
   return fail(PLLB_ERR_INVALID, "gemm: unknown epilogue");
 }

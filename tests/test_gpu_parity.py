@@ -329,6 +329,18 @@ def test_too_long_hypothesis_is_rejected():
             sc.score_packed(np.full(n, 700, np.int32), np.array([0, n], np.int64))
 
 
+def test_out_of_vocabulary_token_is_rejected():
+    from asr_rescoring_b200._lib import PllbError
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 5)
+    with engine.PllScorer(sd, cfg) as sc:
+        for bad in (cfg["vocab"], -1):
+            with pytest.raises(PllbError):
+                sc.score_packed(np.array([700, bad, 701], np.int32), np.array([0, 3], np.int64))
+        ok = sc.score_packed(np.array([700, cfg["vocab"] - 1, 701], np.int32), np.array([0, 3], np.int64))
+        assert np.isfinite(ok).all()
+
+
 def test_drop_in_run_one_epoch_matches_oracle_rows():
     from asr_rescoring_b200.MLM_PLL import main as dropin
     from types import SimpleNamespace
