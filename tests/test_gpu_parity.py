@@ -102,6 +102,27 @@ def test_drop_in_rescore_functions_match_oracle():
         dropin.cer([""], ["a"])
 
 
+def test_other_cer_call_sites_match_oracle():
+    """espnet_data/preprocess/main.py:59-60 (hyps_cer.json) and RMBR's CER utility / mbr_decode."""
+    import torch
+    from asr_rescoring_b200 import cer_clients
+    nb = synth.make_nbest(40, 6, seed=44)
+    got = cer_clients.hyps_cer(nb.hyps_text(), nb.ref_text())
+    for u, r, hs in zip(nb.utt_ids, nb.refs, nb.hyps):
+        for k, h in enumerate(hs):
+            assert got[u][f"hyp_{k + 1}"] == rescore_oracle.cer(r, h)
+    with pytest.raises(ValueError):
+        cer_clients.pair_cer([" "], ["a"])
+
+    class OracleCer(cer_clients.BaseFunction):           # RMBR/utility_functions.py:24-33 on the oracle
+        def score(self, cands, refs):
+            return [1 - rescore_oracle.cer(r, c) for c, r in zip(cands, refs)]
+
+    pred, sc = cer_clients.mbr_decode(5, nb.hyps, cer_clients.CerScoreFunction(None))
+    pred_o, sc_o = cer_clients.mbr_decode(5, nb.hyps, OracleCer(None))
+    assert pred == pred_o and torch.equal(sc, sc_o)
+
+
 def test_combiner_full_size_properties():
     """Config 5 size (7 176 x 50-best, 101 weights): size-independent properties."""
     nb = synth.make_nbest(7176, 50, seed=9)
