@@ -305,6 +305,39 @@ def test_pll_vs_live_oracle_and_rescored_one_best():
     assert (a_o == a_g).mean() >= 0.9
 
 
+def test_config1_100x10_best_against_oracle_acceptance():
+    """BASELINE.json configs[0] (100 utterances x 10-best, random-init bert-base-chinese) run in
+    full through the oracle port of the reference's CPU path and through the GPU path:
+    north_star acceptance — |dPLL| <= 0.05 nats per hypothesis, identical rescored 1-best,
+    identical CER counts at the weight the reference picks."""
+    cfg = synth.BERT_BASE_CHINESE
+    sd = synth.random_init_state_dict(cfg, 10)
+    nb = synth.make_nbest(100, 10, seed=0)
+    tok, off = nb.packed_tokens()
+    n = len(off) - 1
+    hyps = {"u": {f"hyp_{i + 1}": [int(t) for t in tok[off[i]:off[i + 1]]] for i in range(n)}}
+    exp = pll_oracle.score_hyps(sd, cfg, hyps)
+    ref = np.array([exp["u"][f"hyp_{i + 1}"] for i in range(n)])
+    with engine.PllScorer(sd, cfg) as sc:
+        got = sc.score_packed(tok, off)
+    err = np.abs(got - ref)
+    assert err.max() <= PLL_TOL, (err.max(), int((err > PLL_TOL).sum()))
+    assert err.mean() < 0.02
+    from asr_rescoring_b200 import rescore as dropin
+    c = rescore_oracle.config(10)
+    lm_o, lm_g = ref.reshape(100, 10).tolist(), got.reshape(100, 10).tolist()
+    bw_o, cer_o = rescore_oracle.find_best_weight(nb.am.tolist(), lm_o, nb.hyps, nb.refs, c)
+    bw_g, cer_g = dropin.find_best_weight(nb.am.tolist(), lm_g, nb.hyps, nb.refs, c)
+    lens = rescore_oracle.hyps_len_of(nb.hyps, 10)
+    a_o = np.argmax(rescore_oracle.rescore(bw_o, lens, nb.am, np.array(lm_o), c), -1)
+    a_g = np.argmax(rescore_oracle.rescore(bw_o, lens, nb.am, np.array(lm_g), c), -1)
+    assert (a_o == a_g).mean() >= 0.99, (a_o != a_g).sum()     # rescored 1-best at the reference's weight
+    # CER counts with the oracle's PLLs through the GPU combiner are bit-exact
+    bw_x, cer_x = dropin.find_best_weight(nb.am.tolist(), lm_o, nb.hyps, nb.refs, c)
+    assert bw_x == bw_o and cer_x == cer_o
+    assert abs(cer_g - cer_o) <= 2.0 / sum(len(r) for r in nb.refs)
+
+
 def test_scoring_is_deterministic_and_chunking_invariant():
     cfg = synth.BERT_TINY
     sd = synth.random_init_state_dict(cfg, 4, perturb=True)
