@@ -463,11 +463,22 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
   const uint32_t sm_addr = (uint32_t)__cvta_generic_to_shared(sm);
   constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
   __syncwarp();                                           // previous sequence's fragments consumed
-  for (int i = lane; i < 24 * T; i += 32) {               // 3 matrices x T rows x 8 chunks of 16 B
-    const int mat = i / (8 * T), rem = i - mat * 8 * T, r = rem >> 3, ch = rem & 7;
-    const __nv_bfloat16* src = qb + (size_t)r * ld + (size_t)mat * H + ch * 8;
-    const uint32_t dst = sm_addr + (uint32_t)((mat * ATT_TS + r) * ATT_VROW + ch * 8) * 2;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  {
+    // 3 matrices x T rows x 8 chunks of 16 B; lane -> (row offset, chunk), no integer division
+    const int r_off = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int mat = 0; mat < 3; ++mat) {
+      const __nv_bfloat16* src = qb + (size_t)mat * H + ch * 8;
+      const uint32_t dst = sm_addr + (uint32_t)(mat * ATT_TS * ATT_VROW + ch * 8) * 2;
+      for (int r = r_off; r < T; r += 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(r * ATT_VROW) * 2),
+                     "l"(src + (size_t)r * ld) : "memory");
+    }
+    // V rows T .. ceil16(T)-1 are multiplied by p = 0: they must be finite (0 * NaN = NaN).  K / Q
+    // padding rows only produce scores that are replaced by -inf / rows that are never stored.
+    const int t16 = (T + 15) & ~15;
+    for (int r = T + r_off; r < t16; r += 4)
+      *reinterpret_cast<uint4*>(sm + (2 * ATT_TS + r) * ATT_VROW + ch * 8) = make_uint4(0, 0, 0, 0);
   }
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncwarp();
@@ -572,8 +583,6 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   extern __shared__ __align__(16) uint8_t att_dyn[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_dyn) + (size_t)wib * ATT_STAGE_ELEMS;
-  // rows T..31 of the staging area are read as masked keys / unused queries: keep them finite
-  for (int i = lane; i < ATT_STAGE_ELEMS / 8; i += 32) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
   const int64_t pair = (int64_t)blockIdx.x * ATT_WARPS + wib;
   if (pair >= (int64_t)n_copies * NH) return;
   const int c = (int)(pair / NH), head = (int)(pair % NH);
