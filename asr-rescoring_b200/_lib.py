@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint16, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpllb200.so")
+LIB_PATH = os.environ.get("PLLB_LIB") or os.path.join(HERE, "libpllb200.so")   # PLLB_LIB: A/B testing of builds
 
 
 class PllbError(RuntimeError):

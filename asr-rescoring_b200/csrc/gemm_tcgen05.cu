@@ -35,14 +35,20 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
+#ifndef PLLB_GEMM_STAGES
+#define PLLB_GEMM_STAGES 4
+#endif
+#ifndef PLLB_GEMM_EPI_BUFS
+#define PLLB_GEMM_EPI_BUFS 1
+#endif
+constexpr int STAGES = PLLB_GEMM_STAGES;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int EPI_WARPS = 8;                 // two per TMEM lane quarter, each owning half of the BN columns
 constexpr int EPI_COLS = BN / 2;             // columns per epilogue warp
 constexpr int EPI_BUF_BYTES = 32 * 128;      // one 32-row x 128-byte swizzled box
-constexpr int EPI_BUFS = 1;                  // per epilogue warp
+constexpr int EPI_BUFS = PLLB_GEMM_EPI_BUFS;  // per epilogue warp
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;               // 2 accumulator stages x BN columns
 constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
@@ -112,19 +118,31 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
 // MC: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (same
 // weight columns): each CTA fetches half of the 256x64 W box and TMA-multicasts it to both,
 // which halves the L2 -> SM weight traffic; the stage-release barrier then counts both CTAs.
-template <int EPI, bool FP16, bool MC>
+//
+// MODE 2 (cta_group::2): the pair issues ONE tcgen05.mma with M = 256 per k-step from the leader
+// CTA; each CTA keeps its own 128 rows of A and only HALF of the W box (the tensor cores read
+// the other half from the peer's shared memory), so a stage is 32 KiB instead of 48 and the
+// ring is 6 deep; accumulators for rows 0-127 / 128-255 land in the leader's / peer's TMEM.
+// Both CTAs' TMA loads complete on the leader's full barrier; the MMA's commits are multicast
+// to both CTAs (stage release, accumulator ready); both epilogues report back to the leader.
+template <int EPI, bool FP16, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
+  constexpr bool MC = MODE == 1;
+  constexpr bool TWO = MODE == 2;
+  constexpr int NST = TWO ? (STAGES * 3) / 2 : STAGES;                 // 6 x 32 KiB or 4 x 48 KiB
+  constexpr int B_BYTES = TWO ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+  static_assert(NST * (A_STAGE_BYTES + B_BYTES) <= SMEM_PIPE, "operand ring exceeds its budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t sB = smem_base + NST * A_STAGE_BYTES;
   const uint32_t sEpi = smem_base + SMEM_PIPE;
   const uint32_t sBar = sEpi + SMEM_EPI;
-  const uint32_t bar_full = sBar;                 // STAGES x 8 B
-  const uint32_t bar_empty = sBar + 8 * STAGES;   // STAGES x 8 B
-  const uint32_t bar_tfull = sBar + 16 * STAGES;  // 2 x 8 B
+  const uint32_t bar_full = sBar;                 // NST x 8 B
+  const uint32_t bar_empty = sBar + 8 * NST;      // NST x 8 B
+  const uint32_t bar_tfull = sBar + 16 * NST;     // 2 x 8 B
   const uint32_t bar_tempty = bar_tfull + 16;     // 2 x 8 B
   const uint32_t tmem_slot = bar_tempty + 16;     // 4 B
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -135,11 +153,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_m = (p.M + BM - 1) / BM;
   const int num_kb = p.K / BK;
   // work units: one tile per CTA, or (MC) a pair of vertically adjacent tiles per cluster
-  const uint32_t crank = MC ? cluster_ctarank() : 0;
-  const int unit0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_stride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int num_tiles = (MC ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
-#define PLLB_TILE_M(tile) ((MC ? 2 * ((tile) / tiles_n) + (int)crank : (tile) / tiles_n) * BM)
+  constexpr bool PAIR = MC || TWO;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = (PAIR ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+#define PLLB_TILE_M(tile) ((PAIR ? 2 * ((tile) / tiles_n) + (int)crank : (tile) / tiles_n) * BM)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -148,23 +167,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < NST; ++s) {
         mbar_init(bar_full + 8 * s, 1);
         mbar_init(bar_empty + 8 * s, MC ? 2 : 1);           // MC: both CTAs' MMAs must have retired
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
-        mbar_init(bar_tempty + 8 * s, EPI_WARPS);
+        mbar_init(bar_tempty + 8 * s, TWO ? 2 * EPI_WARPS : EPI_WARPS);   // TWO: both CTAs' epilogues
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();       // the peer's barriers exist before anything is multicast to them
+  if (PAIR) cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -177,6 +201,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if constexpr (TWO) {
+            // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
+            const uint32_t lead_full = mapa_shared(bar_full + 8 * stage, 0);
+            if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (A_STAGE_BYTES + B_BYTES));
+            tma_load_2d_2sm(sA + stage * A_STAGE_BYTES, &tmA, lead_full, kb * BK, m0);
+            tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, n0 + (int)crank * (BN / 2));
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
           tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m0);
           if constexpr (MC) {
@@ -185,14 +218,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                   kb * BK, n0 + (int)crank * (BN / 2), (uint16_t)0x3);
           } else
           tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = FP16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
+    if (lane == 0 && (!TWO || crank == 0)) {                 // TWO: the leader issues for the pair
+      constexpr int MMA_M = TWO ? 2 * BM : BM;
+      constexpr uint32_t idesc = FP16 ? make_idesc_f16(MMA_M, BN) : make_idesc_bf16(MMA_M, BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
@@ -202,18 +236,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(bar_full + 8 * stage, phase);         // TMA bytes landed
           tcgen05_fence_after();
           const uint32_t a_addr = sA + stage * A_STAGE_BYTES;
-          const uint32_t b_addr = sB + stage * B_STAGE_BYTES;
+          const uint32_t b_addr = sB + stage * B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2);
             const uint64_t bdesc = make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2);
-            tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (TWO) tcgen05_mma_bf16_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else tcgen05_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if constexpr (MC) tcgen05_commit_multicast(bar_empty + 8 * stage, (uint16_t)0x3);
-          else tcgen05_commit(bar_empty + 8 * stage);     // smem stage reusable once MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          // smem stage reusable once the MMAs retire (in every CTA that holds a part of it)
+          if constexpr (TWO) tcgen05_commit_2cta_multicast(bar_empty + 8 * stage, (uint16_t)0x3);
+          else if constexpr (MC) tcgen05_commit_multicast(bar_empty + 8 * stage, (uint16_t)0x3);
+          else tcgen05_commit(bar_empty + 8 * stage);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(bar_tfull + 8 * acc);              // accumulator complete
+        // accumulator complete (TWO: both CTAs' epilogues read their own 128 rows)
+        if constexpr (TWO) tcgen05_commit_2cta_multicast(bar_tfull + 8 * acc, (uint16_t)0x3);
+        else tcgen05_commit(bar_tfull + 8 * acc);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -224,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp - 2;
     const int cbase = (ew >> 2) * EPI_COLS;               // first tile column owned by this warp
     const uint32_t my_buf = sEpi + ew * EPI_BUFS * EPI_BUF_BYTES;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, buf_i = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int m0 = PLLB_TILE_M(tile);
       const int tn = tile % tiles_n;
@@ -272,9 +311,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32b_x32(t_addr + c0, r0);
           tmem_ld_32x32b_x32(t_addr + c0 + 32, r1);
           tcgen05_wait_ld();
-          const uint32_t buf = my_buf;
-          if (lane == 0) tma_store_wait_read<0>();         // the store that last read this buffer is done
+          const uint32_t buf = my_buf + (buf_i % EPI_BUFS) * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();   // the store that last read this buffer is done
           __syncwarp();
+          ++buf_i;
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                    // 8 chunks of 8 bf16 (16 B)
@@ -312,9 +352,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_addr + c0, r);
           tcgen05_wait_ld();
-          const uint32_t buf = my_buf;
-          if (lane == 0) tma_store_wait_read<0>();
+          const uint32_t buf = my_buf + (buf_i % EPI_BUFS) * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();
           __syncwarp();
+          ++buf_i;
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                    // 8 chunks of 4 fp32 (16 B)
@@ -342,7 +383,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // all tcgen05.ld of this accumulator have completed (wait::ld above): release it
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's MMA waits for both
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -351,11 +395,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();       // the peer may still multicast-arrive on this CTA's barriers
+  if (PAIR) cluster_sync_all();     // the peer may still multicast-arrive on this CTA's barriers
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (TWO) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 #undef PLLB_TILE_M
 }
@@ -394,12 +439,12 @@ int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_
   return PLLB_OK;
 }
 
-template <int EPI, bool FP16, bool MC>
+template <int EPI, bool FP16, int MODE>
 int launch_epi3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<EPI, FP16, MC>;
+  auto kern = gemm_tcgen05_kernel<EPI, FP16, MODE>;
   PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-  if constexpr (MC) {
+  if constexpr (MODE != 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
@@ -422,21 +467,23 @@ int launch_epi3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
 }
 template <int EPI>
 int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid, bool fp16,
-               bool mc, cudaStream_t stream) {
-  if (mc)
-    return fp16 ? launch_epi3<EPI, true, true>(a, b, c, kp, grid, stream)
-                : launch_epi3<EPI, false, true>(a, b, c, kp, grid, stream);
-  return fp16 ? launch_epi3<EPI, true, false>(a, b, c, kp, grid, stream)
-              : launch_epi3<EPI, false, false>(a, b, c, kp, grid, stream);
+               int mode, cudaStream_t stream) {
+  if (mode == 2)
+    return fp16 ? launch_epi3<EPI, true, 2>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 2>(a, b, c, kp, grid, stream);
+  if (mode == 1)
+    return fp16 ? launch_epi3<EPI, true, 1>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 1>(a, b, c, kp, grid, stream);
+  return fp16 ? launch_epi3<EPI, true, 0>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 0>(a, b, c, kp, grid, stream);
 }
 
-bool multicast_enabled() {
+// 0 = one CTA per tile, 1 = CTA pairs with TMA multicast of W, 2 = cta_group::2 MMA (default)
+int pair_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("PLLB_GEMM_MULTICAST");
-    v = e ? (atoi(e) != 0) : 1;
+    const char* e = getenv("PLLB_GEMM_MODE");
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 2) v = 2;
   }
-  return v != 0;
+  return v;
 }
 
 }  // namespace
@@ -449,7 +496,8 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
-  const bool mc = multicast_enabled() && M > BM;         // pairs of vertically adjacent tiles share W
+  const int mode = M > BM ? pair_mode() : 0;             // pairs of vertically adjacent tiles share W
+  const bool mc = mode != 0;
   if ((rc = make_tmap(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, mc ? BN / 2 : BN, BK))) return rc;
   tc = ta;
   if (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16) {
@@ -473,11 +521,11 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
     grid = (int)(tiles < sm_count() ? tiles : sm_count());
   }
   switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, fp16, mc, stream);
-    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, fp16, mc, stream);
-    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, fp16, mc, stream);
-    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, fp16, mc, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, fp16, mc, stream);
+    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, fp16, mode, stream);
+    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, fp16, mode, stream);
+    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, fp16, mode, stream);
+    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, fp16, mode, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, fp16, mode, stream);
   }
   return fail(PLLB_ERR_INVALID, "gemm: unknown epilogue");
 }
