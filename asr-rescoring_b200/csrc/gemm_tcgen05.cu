@@ -131,15 +131,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
   constexpr bool MC = MODE == 1;
   constexpr bool TWO = MODE == 2;
-  constexpr int NST = TWO ? (STAGES * 3) / 2 : STAGES;                 // 6 x 32 KiB or 4 x 48 KiB
+  // TWO: 5 x 32 KiB operand stages + two staging boxes per epilogue warp; else 4 x 48 KiB + one box
+  constexpr int NST = TWO ? 5 : STAGES;
   constexpr int B_BYTES = TWO ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
-  static_assert(NST * (A_STAGE_BYTES + B_BYTES) <= SMEM_PIPE, "operand ring exceeds its budget");
+  constexpr int EBUFS = TWO ? 2 : EPI_BUFS;
+  constexpr int PIPE_BYTES = NST * (A_STAGE_BYTES + B_BYTES);
+  static_assert(PIPE_BYTES + EPI_WARPS * EBUFS * EPI_BUF_BYTES <= SMEM_PIPE + SMEM_EPI, "shared memory budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + NST * A_STAGE_BYTES;
-  const uint32_t sEpi = smem_base + SMEM_PIPE;
-  const uint32_t sBar = sEpi + SMEM_EPI;
+  const uint32_t sEpi = smem_base + PIPE_BYTES;
+  const uint32_t sBar = smem_base + SMEM_PIPE + SMEM_EPI;
   const uint32_t bar_full = sBar;                 // NST x 8 B
   const uint32_t bar_empty = sBar + 8 * NST;      // NST x 8 B
   const uint32_t bar_tfull = sBar + 16 * NST;     // 2 x 8 B
@@ -262,7 +265,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;                               // TMEM lane quarter this warp may read
     const int ew = warp - 2;
     const int cbase = (ew >> 2) * EPI_COLS;               // first tile column owned by this warp
-    const uint32_t my_buf = sEpi + ew * EPI_BUFS * EPI_BUF_BYTES;
+    const uint32_t my_buf = sEpi + ew * EBUFS * EPI_BUF_BYTES;
     uint32_t acc = 0, acc_phase = 0, buf_i = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int m0 = PLLB_TILE_M(tile);
@@ -311,8 +314,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32b_x32(t_addr + c0, r0);
           tmem_ld_32x32b_x32(t_addr + c0 + 32, r1);
           tcgen05_wait_ld();
-          const uint32_t buf = my_buf + (buf_i % EPI_BUFS) * EPI_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();   // the store that last read this buffer is done
+          const uint32_t buf = my_buf + (buf_i % EBUFS) * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<EBUFS - 1>();      // the store that last read this buffer is done
           __syncwarp();
           ++buf_i;
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
@@ -352,8 +355,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_addr + c0, r);
           tcgen05_wait_ld();
-          const uint32_t buf = my_buf + (buf_i % EPI_BUFS) * EPI_BUF_BYTES;
-          if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();
+          const uint32_t buf = my_buf + (buf_i % EBUFS) * EPI_BUF_BYTES;
+          if (lane == 0) tma_store_wait_read<EBUFS - 1>();
           __syncwarp();
           ++buf_i;
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
