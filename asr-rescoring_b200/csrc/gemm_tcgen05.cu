@@ -478,15 +478,19 @@ int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
   return fp16 ? launch_epi3<EPI, true, 0>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 0>(a, b, c, kp, grid, stream);
 }
 
-// 0 = one CTA per tile, 1 = CTA pairs with TMA multicast of W, 2 = cta_group::2 MMA (default)
-int pair_mode() {
-  static int v = -1;
-  if (v < 0) {
+// 0 = one CTA per tile, 1 = CTA pairs with TMA multicast of W, 2 = cta_group::2 MMA.
+// Default: cta_group::2, except for the GELU epilogue — FFN1 is paced by its epilogue's CUDA-core
+// math, where the cluster-scope accumulator hand-back of mode 2 costs more than the deeper
+// operand ring gains (measured ABAB inside the C2 step: QKV 671 vs 727 ms, FFN1 905-918 vs 884 ms).
+int pair_mode(int epilogue) {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("PLLB_GEMM_MODE");
-    v = e ? atoi(e) : 2;
-    if (v < 0 || v > 2) v = 2;
+    v = e ? atoi(e) : -1;
+    if (v < -1 || v > 2) v = -1;
   }
-  return v;
+  if (v >= 0) return v;
+  return epilogue == EPI_BIAS_GELU_BF16 ? 1 : 2;
 }
 
 }  // namespace
@@ -499,7 +503,7 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
-  const int mode = M > BM ? pair_mode() : 0;             // pairs of vertically adjacent tiles share W
+  const int mode = M > BM ? pair_mode(epilogue) : 0;             // pairs of vertically adjacent tiles share W
   const bool mc = mode != 0;
   if ((rc = make_tmap(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, mc ? BN / 2 : BN, BK))) return rc;
   tc = ta;
