@@ -53,6 +53,8 @@ SIGNATURES = {
     "pllb_workspace_bytes": (c_int64, [c_void_p]),
     "pllb_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "pllb_score_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "pllb_score_cls": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_float, c_void_p, c_void_p]),
+    "pllb_score_cls_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_float, c_void_p]),
     "pllb_expand": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pllb_get_stats": (c_int, [c_void_p, POINTER(Stats)]),
     "pllb_reset_stats": (c_int, [c_void_p]),

@@ -44,6 +44,12 @@ struct LayerDev {
   float *qkv_b, *ao_b, *ao_g, *ao_be, *ff1_b, *ff2_b, *out_g, *out_be;
 };
 
+struct ClsHead {        // Linear(H, 1) applied to the [CLS] state (device pointers)
+  const float* w;
+  float b;
+  float* out;
+};
+
 struct TimedLaunch {
   cudaEvent_t start, stop;
   int kind;
@@ -55,6 +61,7 @@ struct pllb_context {
   pllb_model_desc d{};
   int device = 0;
   bool fp16 = false;                 // GEMM operand dtype: bf16 (default) or IEEE fp16
+  bool has_head = false;             // MLM head weights were supplied (PLL scoring available)
   bool fused_ln = true;              // residual + LayerNorm inside the GEMM epilogue (PLLB_FUSED_LN=0 disables)
   int64_t cap_rows = 0, cap_copies = 0, cap_hyps = 0;
   int vocab_pad = 0, tiles_v = 0;
@@ -182,10 +189,11 @@ int timed_gemm_ln(pllb_context* c, int kind, const void* A, const void* W, const
 // n_hyp+1 int32) already sits in device memory.  upto_layer < 0: full scoring.
 int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, const int32_t* copy_base,
               const int32_t* row_base, int32_t n_hyp, int32_t n_copies, int64_t n_rows, int max_T, double* out_pll,
-              float* out_tok_logp, int upto_layer, cudaStream_t s) {
+              float* out_tok_logp, int upto_layer, cudaStream_t s, const ClsHead* cls = nullptr,
+              float* out_cls = nullptr) {
   const pllb_model_desc& d = c->d;
   const int H = d.hidden, I = d.intermediate;
-  RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, d.vocab, c->plan, s));
+  RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, d.vocab, cls != nullptr, c->plan, s));
   RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
                      d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->hidden_bf16, c->fp16, s));
   RC(launch_rowmajor_to_t32(c->y_f32, c->hidden_f32, n_rows, H, s));
@@ -212,6 +220,12 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
     RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hidden_f32, c->hidden_bf16, n_rows, I, s));
   }
   if (upto_layer >= 0) return PLLB_OK;
+  if (cls) {
+    // RescoreBert: lm_score = Linear(H, 1)(last_hidden_state[:, 0, :]) — RescoreBert/model.py:13-21.
+    // The pruned last layer left the final [CLS] states in hid_c (fp32, T32 layout).
+    if (!prune_last) return fail(PLLB_ERR_INVALID, "sequence scoring needs at least one encoder layer");
+    return launch_cls_linear(c->hid_c, cls->w, cls->b, n_copies, H, out_cls, s);
+  }
   // MLM head at the masked row of every copy only (the reference evaluates all B*T rows,
   // transformers modeling_bert.py:975, and keeps one: MLM_PLL/main.py:101).
   if (!prune_last) RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->t_bf16, s));
@@ -248,8 +262,10 @@ int ensure_meta(pllb_context* c, int64_t need, cudaStream_t s) {
 
 // Plans chunks on the host (offsets are control metadata), uploads the metadata once and
 // enqueues every chunk on `s` without synchronising.
+// cls != nullptr: sequence-level scoring ([CLS] t [SEP], one pass per hypothesis, Linear(H,1)
+// on the [CLS] state) instead of masked-copy PLL scoring.
 int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, int32_t n_hyp, double* out_pll,
-               float* out_tok_logp, int upto_layer, float* out_hidden, cudaStream_t s) {
+               float* out_tok_logp, int upto_layer, float* out_hidden, cudaStream_t s, const ClsHead* cls = nullptr) {
   if (!c) return fail(PLLB_ERR_INVALID, "null handle");
   if (n_hyp < 0 || (n_hyp > 0 && (!off || !hyp_tokens && off[n_hyp] > off[0])))
     return fail(PLLB_ERR_INVALID, "pllb_score: null argument");
@@ -266,15 +282,16 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
       if (L + 2 > c->d.max_position)
         return fail(PLLB_ERR_TOO_LONG, "hypothesis " + std::to_string(h) + " has " + std::to_string(L) +
                                            " tokens; max_position_embeddings allows " + std::to_string(c->d.max_position - 2));
-      const int64_t rows = L * (L + 2);
-      if (rows > c->cap_rows || L > c->cap_copies)
+      const int64_t rows = cls ? L + 2 : L * (L + 2);
+      const int64_t copies = cls ? 1 : L;
+      if (rows > c->cap_rows || copies > c->cap_copies)
         return fail(PLLB_ERR_OOM, "a single hypothesis exceeds max_chunk_tokens");
-      if (cur.n_hyp > 0 && (cur.n_rows + rows > c->cap_rows || cur.n_copies + L > c->cap_copies || cur.n_hyp + 1 > c->cap_hyps)) {
+      if (cur.n_hyp > 0 && (cur.n_rows + rows > c->cap_rows || cur.n_copies + copies > c->cap_copies || cur.n_hyp + 1 > c->cap_hyps)) {
         chunks.push_back(cur);
         cur = Chunk{h, 0, 0, 0, off[h], 0, 0};
       }
       cur.n_hyp += 1;
-      cur.n_copies += (int32_t)L;
+      cur.n_copies += (int32_t)copies;
       cur.n_rows += rows;
       cur.max_T = std::max(cur.max_T, (int)L + 2);
     }
@@ -296,7 +313,7 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
       tok_off[i] = (int32_t)t; copy_base[i] = (int32_t)cb; row_base[i] = (int32_t)rb;
       if (i < ch.n_hyp) {
         const int64_t L = off[ch.hyp_begin + i + 1] - off[ch.hyp_begin + i];
-        t += L; cb += L; rb += L * (L + 2);
+        t += L; cb += cls ? 1 : L; rb += cls ? L + 2 : L * (L + 2);
       }
     }
   }
@@ -312,7 +329,8 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
     const int32_t* row_base = copy_base + (ch.n_hyp + 1);
     RC(run_chunk(c, hyp_tokens + (ch.tok_begin - off[0]), tok_off, copy_base, row_base, ch.n_hyp, ch.n_copies, ch.n_rows,
                  ch.max_T, out_pll ? out_pll + ch.hyp_begin : nullptr,
-                 out_tok_logp ? out_tok_logp + (ch.tok_begin - off[0]) : nullptr, upto_layer, s));
+                 out_tok_logp ? out_tok_logp + (ch.tok_begin - off[0]) : nullptr, upto_layer, s, cls,
+                 cls ? cls->out + ch.hyp_begin : nullptr));
     if (out_hidden) RC(launch_t32_to_rowmajor(c->hidden_f32, out_hidden, ch.n_rows, c->d.hidden, s));
     c->stats.chunks += 1;
     c->stats.hyps_scored += ch.n_hyp;
@@ -453,18 +471,22 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
     TRY(copy_f32(c, &L.out_g, lw.out_ln_g, H, s));
     TRY(copy_f32(c, &L.out_be, lw.out_ln_b, H, s));
   }
-  TRY(conv_bf16(c, &c->head_w, w->head_w, (int64_t)H * H, s));
-  TRY(copy_f32(c, &c->head_b, w->head_b, H, s));
-  TRY(copy_f32(c, &c->head_g, w->head_ln_g, H, s));
-  TRY(copy_f32(c, &c->head_be, w->head_ln_b, H, s));
   c->vocab_pad = (int)align_up(V, 256);
   c->tiles_v = c->vocab_pad / 256;
-  TRY(dev_alloc(c, &c->dec_w, (int64_t)c->vocab_pad * H));
-  cudaMemsetAsync(c->dec_w, 0, sizeof(__nv_bfloat16) * (size_t)c->vocab_pad * H, s);
-  TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->fp16, s));
-  TRY(dev_alloc(c, &c->dec_b, c->vocab_pad));
-  cudaMemsetAsync(c->dec_b, 0, sizeof(float) * c->vocab_pad, s);
-  cudaMemcpyAsync(c->dec_b, w->decoder_b, sizeof(float) * V, cudaMemcpyDeviceToDevice, s);
+  // the MLM head is optional: a RescoreBert checkpoint (BertModel + Linear) has none
+  c->has_head = w->head_w && w->head_b && w->head_ln_g && w->head_ln_b && w->decoder_w && w->decoder_b;
+  if (c->has_head) {
+    TRY(conv_bf16(c, &c->head_w, w->head_w, (int64_t)H * H, s));
+    TRY(copy_f32(c, &c->head_b, w->head_b, H, s));
+    TRY(copy_f32(c, &c->head_g, w->head_ln_g, H, s));
+    TRY(copy_f32(c, &c->head_be, w->head_ln_b, H, s));
+    TRY(dev_alloc(c, &c->dec_w, (int64_t)c->vocab_pad * H));
+    cudaMemsetAsync(c->dec_w, 0, sizeof(__nv_bfloat16) * (size_t)c->vocab_pad * H, s);
+    TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->fp16, s));
+    TRY(dev_alloc(c, &c->dec_b, c->vocab_pad));
+    cudaMemsetAsync(c->dec_b, 0, sizeof(float) * c->vocab_pad, s);
+    cudaMemcpyAsync(c->dec_b, w->decoder_b, sizeof(float) * V, cudaMemcpyDeviceToDevice, s);
+  }
 
   // workspace: sized by the expanded-token budget of one chunk
   if (max_chunk_tokens <= 0) max_chunk_tokens = (int64_t)1 << 20;
@@ -521,6 +543,7 @@ int64_t pllb_workspace_bytes(pllb_handle h) { return h ? h->owned_bytes : 0; }
 int pllb_score(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets, int32_t n_hyp, double* out_pll,
                float* out_token_logp, void* stream) {
   if (!out_pll && n_hyp > 0) return fail(PLLB_ERR_INVALID, "pllb_score: out_pll is null");
+  if (h && !h->has_head) return fail(PLLB_ERR_INVALID, "pllb_score: the handle was created without MLM head weights");
   if (n_hyp > 0 && !hyp_offsets) return fail(PLLB_ERR_INVALID, "pllb_score: hyp_offsets is null");
   const int64_t o0 = n_hyp > 0 ? hyp_offsets[0] : 0;   // tokens / token_logp are indexed by absolute offset
   return score_impl(h, hyp_tokens ? hyp_tokens + o0 : nullptr, hyp_offsets, n_hyp, out_pll,
@@ -532,6 +555,7 @@ int pllb_score_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off
   if (!h) return fail(PLLB_ERR_INVALID, "null handle");
   if (n_hyp <= 0) return PLLB_OK;
   if (!off || !out_pll) return fail(PLLB_ERR_INVALID, "pllb_score_host: null argument");
+  if (!h->has_head) return fail(PLLB_ERR_INVALID, "pllb_score_host: the handle was created without MLM head weights");
   PLLB_CUDA(cudaSetDevice(h->device));
   const int64_t n_tok = off[n_hyp] - off[0];
   if (n_tok > 0 && !hyp_tokens) return fail(PLLB_ERR_INVALID, "pllb_score_host: hyp_tokens is null");
@@ -555,6 +579,44 @@ int pllb_score_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off
   PLLB_CUDA(cudaMemcpyAsync(out_pll, d_pll, sizeof(double) * n_hyp, cudaMemcpyDeviceToHost, s));
   if (out_token_logp && n_tok > 0)
     PLLB_CUDA(cudaMemcpyAsync(out_token_logp + off[0], d_lp, sizeof(float) * n_tok, cudaMemcpyDeviceToHost, s));
+  PLLB_CUDA(cudaStreamSynchronize(s));
+  return PLLB_OK;
+}
+
+int pllb_score_cls(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets, int32_t n_hyp,
+                   const float* linear_w, float linear_b, float* out_scores, void* stream) {
+  if (n_hyp > 0 && (!hyp_offsets || !linear_w || !out_scores)) return fail(PLLB_ERR_INVALID, "pllb_score_cls: null argument");
+  const int64_t o0 = n_hyp > 0 ? hyp_offsets[0] : 0;
+  ClsHead cls{linear_w, linear_b, out_scores};
+  return score_impl(h, hyp_tokens ? hyp_tokens + o0 : nullptr, hyp_offsets, n_hyp, nullptr, nullptr, -1, nullptr,
+                    (cudaStream_t)stream, &cls);
+}
+
+int pllb_score_cls_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, int32_t n_hyp,
+                        const float* linear_w, float linear_b, float* out_scores) {
+  if (!h) return fail(PLLB_ERR_INVALID, "null handle");
+  if (n_hyp <= 0) return PLLB_OK;
+  if (!off || !linear_w || !out_scores) return fail(PLLB_ERR_INVALID, "pllb_score_cls_host: null argument");
+  PLLB_CUDA(cudaSetDevice(h->device));
+  const int64_t n_tok = off[n_hyp] - off[0];
+  if (n_tok > 0 && !hyp_tokens) return fail(PLLB_ERR_INVALID, "pllb_score_cls_host: hyp_tokens is null");
+  for (int64_t i = off[0]; i < off[n_hyp]; ++i)
+    if (hyp_tokens[i] < 0 || hyp_tokens[i] >= h->d.vocab)
+      return fail(PLLB_ERR_INVALID, "token id " + std::to_string(hyp_tokens[i]) + " is outside the vocabulary");
+  const int H = h->d.hidden;
+  const int64_t b_tok = align_up(sizeof(int32_t) * std::max<int64_t>(n_tok, 1), 256);
+  const int64_t b_out = align_up(sizeof(float) * n_hyp, 256), b_w = align_up(sizeof(float) * H, 256);
+  RC(ensure_io(h, b_tok + b_out + b_w));
+  uint8_t* base = reinterpret_cast<uint8_t*>(h->io_dev);
+  int32_t* d_tok = reinterpret_cast<int32_t*>(base);
+  float* d_out = reinterpret_cast<float*>(base + b_tok);
+  float* d_w = reinterpret_cast<float*>(base + b_tok + b_out);
+  cudaStream_t s = 0;
+  if (n_tok > 0) PLLB_CUDA(cudaMemcpyAsync(d_tok, hyp_tokens + off[0], sizeof(int32_t) * n_tok, cudaMemcpyHostToDevice, s));
+  PLLB_CUDA(cudaMemcpyAsync(d_w, linear_w, sizeof(float) * H, cudaMemcpyHostToDevice, s));
+  ClsHead cls{d_w, linear_b, d_out};
+  RC(score_impl(h, d_tok, off, n_hyp, nullptr, nullptr, -1, nullptr, s, &cls));
+  PLLB_CUDA(cudaMemcpyAsync(out_scores, d_out, sizeof(float) * n_hyp, cudaMemcpyDeviceToHost, s));
   PLLB_CUDA(cudaStreamSynchronize(s));
   return PLLB_OK;
 }
@@ -586,7 +648,7 @@ int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, in
   const int32_t* d_tok_off = h->meta_dev;
   hyp_tokens += off[0];
   RC(launch_expand_plan(hyp_tokens, d_tok_off, d_tok_off + (n_hyp + 1), d_tok_off + 2 * (n_hyp + 1), n_hyp, h->d.vocab,
-                        h->plan, s));
+                        false, h->plan, s));
   RC(launch_expand_ids(hyp_tokens, d_tok_off, h->plan, (int32_t)copies, h->d.cls_id, h->d.sep_id, h->d.mask_id, out_ids,
                        out_mask_pos, out_labels, s));
   return PLLB_OK;

@@ -86,7 +86,8 @@ struct CopyPlan {          // device arrays, one entry per masked copy of the ch
 };
 
 int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
-                       const int32_t* hyp_row_base, int32_t n_hyp, int32_t vocab, CopyPlan plan, cudaStream_t s);
+                       const int32_t* hyp_row_base, int32_t n_hyp, int32_t vocab, bool whole_sequence, CopyPlan plan,
+                       cudaStream_t s);
 int launch_expand_ids(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan plan, int32_t n_copies,
                       int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t* out_ids, int32_t* out_mask_pos,
                       int32_t* out_labels, cudaStream_t s);
@@ -107,6 +108,7 @@ int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, i
 int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out,
                             cudaStream_t s);
 int launch_gather_rows_f32(const float* src, const int32_t* rows, int32_t n, int H, float* out, cudaStream_t s);
+int launch_cls_linear(const float* hid_t32, const float* w, float b, int32_t n, int H, float* out, cudaStream_t s);
 int launch_lse_finish(const float2* partials, const float* label_logit, int32_t n_copies, int n_tiles,
                       float* tok_logp, cudaStream_t s);
 int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
 // One thread per hypothesis: writes the descriptors of its L masked copies.
 __global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off,
                                    const int32_t* __restrict__ hyp_copy_base, const int32_t* __restrict__ hyp_row_base,
-                                   int32_t n_hyp, int32_t vocab, CopyPlan plan) {
+                                   int32_t n_hyp, int32_t vocab, bool whole_sequence, CopyPlan plan) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= n_hyp) return;
   const int t0 = hyp_tok_off[h];
@@ -54,6 +54,17 @@ __global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int
   const int T = L + 2;
   const int c0 = hyp_copy_base[h];
   const int r0 = hyp_row_base[h];
+  if (whole_sequence) {
+    // sequence-level scoring: ONE unmasked copy [CLS] t [SEP]; "mask_row" = the [CLS] row, so
+    // copy_token_id never substitutes [MASK] (position 0 is [CLS]) and the last-layer pruning
+    // gathers exactly the row the Linear(H,1) head reads (RescoreBert/model.py:19).
+    plan.seq_start[c0] = r0;
+    plan.seq_len[c0] = T;
+    plan.mask_row[c0] = r0;
+    plan.label[c0] = 0;
+    plan.hyp[c0] = h;
+    return;
+  }
   for (int m = 0; m < L; ++m) {
     const int c = c0 + m;
     plan.seq_start[c] = r0 + m * T;
@@ -652,6 +663,24 @@ __global__ void t32_to_rowmajor_kernel(const float* __restrict__ src, float* __r
   for (int i = lane; i < G; i += 32) d[i] = s[(size_t)i * 32];
 }
 
+// out[c] = dot(hidden[c, :], w) + b on the T32-layout fp32 rows; one warp per row.
+__global__ void cls_linear_kernel(const float* __restrict__ hid_t32, const float* __restrict__ w, float b, int32_t n, int H,
+                                  float* __restrict__ out) {
+  const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n) return;
+  const int G = H / 4;
+  const float4* row = reinterpret_cast<const float4*>(hid_t32) + (size_t)(c >> 5) * G * 32 + (c & 31);
+  float acc = 0.f;
+  for (int g = lane; g < G; g += 32) {
+    const float4 x = row[(size_t)g * 32];
+    const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + g);
+    acc += (x.x * ww.x + x.y * ww.y) + (x.z * ww.z + x.w * ww.w);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[c] = acc + b;
+}
+
 // log_softmax(logits)[label] = label_logit - (max + log(sum exp)) — MLM_PLL/main.py:101-105
 __global__ void lse_finish_kernel(const float2* __restrict__ partials, const float* __restrict__ label_logit,
                                   int32_t n_copies, int n_tiles, float* __restrict__ tok_logp) {
@@ -707,10 +736,11 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 
 // ------------------------------------------------------------------ launchers
 int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
-                       const int32_t* hyp_row_base, int32_t n_hyp, int32_t vocab, CopyPlan plan, cudaStream_t s) {
+                       const int32_t* hyp_row_base, int32_t n_hyp, int32_t vocab, bool whole_sequence, CopyPlan plan,
+                       cudaStream_t s) {
   if (n_hyp <= 0) return PLLB_OK;
   expand_plan_kernel<<<(unsigned)ceil_div(n_hyp, 128), 128, 0, s>>>(tokens, hyp_tok_off, hyp_copy_base, hyp_row_base,
-                                                                   n_hyp, vocab, plan);
+                                                                   n_hyp, vocab, whole_sequence, plan);
   PLLB_LAUNCH_CHECK("expand_plan_kernel");
   return PLLB_OK;
 }
@@ -829,6 +859,13 @@ int launch_gather_rows_f32(const float* src, const int32_t* rows, int32_t n, int
   if (n <= 0) return PLLB_OK;
   gather_rows_f32_kernel<<<(unsigned)ceil_div(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(src, rows, n, H, out);
   PLLB_LAUNCH_CHECK("gather_rows_f32_kernel");
+  return PLLB_OK;
+}
+
+int launch_cls_linear(const float* hid_t32, const float* w, float b, int32_t n, int H, float* out, cudaStream_t s) {
+  if (n <= 0) return PLLB_OK;
+  cls_linear_kernel<<<(unsigned)ceil_div(n, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(hid_t32, w, b, n, H, out);
+  PLLB_LAUNCH_CHECK("cls_linear_kernel");
   return PLLB_OK;
 }
 

@@ -65,14 +65,17 @@ class PllScorer:
         w.emb_ln_g = dp("bert.embeddings.LayerNorm.weight")
         w.emb_ln_b = dp("bert.embeddings.LayerNorm.bias")
         w.layers = ctypes.cast(layers, ctypes.POINTER(LayerWeights))
-        w.head_w = dp("cls.predictions.transform.dense.weight")
-        w.head_b = dp("cls.predictions.transform.dense.bias")
-        w.head_ln_g = dp("cls.predictions.transform.LayerNorm.weight")
-        w.head_ln_b = dp("cls.predictions.transform.LayerNorm.bias")
-        dec_w = "cls.predictions.decoder.weight" if "cls.predictions.decoder.weight" in state_dict \
-            else "bert.embeddings.word_embeddings.weight"
-        w.decoder_w = dp(dec_w)
-        w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
+        # the MLM head is optional: a RescoreBert checkpoint (BertModel + Linear(H, 1)) has none
+        self.has_mlm_head = "cls.predictions.transform.dense.weight" in state_dict
+        if self.has_mlm_head:
+            w.head_w = dp("cls.predictions.transform.dense.weight")
+            w.head_b = dp("cls.predictions.transform.dense.bias")
+            w.head_ln_g = dp("cls.predictions.transform.LayerNorm.weight")
+            w.head_ln_b = dp("cls.predictions.transform.LayerNorm.bias")
+            dec_w = "cls.predictions.decoder.weight" if "cls.predictions.decoder.weight" in state_dict \
+                else "bert.embeddings.word_embeddings.weight"
+            w.decoder_w = dp(dec_w)
+            w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
         d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
                       self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id,
                       {"bf16": 0, "fp16": 1}[operand_dtype])
@@ -134,6 +137,20 @@ class PllScorer:
                                    ctypes.c_void_p(out.data_ptr()),
                                    ctypes.c_void_p(token_logp.data_ptr()) if token_logp is not None else None,
                                    ctypes.c_void_p(stream)))
+        return out
+
+    def score_cls_packed(self, tokens: np.ndarray, offsets: np.ndarray, linear_w, linear_b: float) -> np.ndarray:
+        """Sequence-level scores (RescoreBert/model.py:13-21): every hypothesis runs through the
+        encoder once as [CLS] t [SEP]; returns float32[n_hyp] = Linear(H,1)([CLS] state)."""
+        offsets = self._check_packed(tokens, offsets)
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        lw = np.ascontiguousarray(np.asarray(linear_w, np.float32).reshape(-1))
+        if lw.shape[0] != self.cfg["hidden"]:
+            raise ValueError("linear_w must have `hidden` elements")
+        n = len(offsets) - 1
+        out = np.zeros(n, np.float32)
+        check(self._lib.pllb_score_cls_host(self._h, _np_ptr(tokens), _np_ptr(offsets), n, _np_ptr(lw),
+                                            float(linear_b), _np_ptr(out)))
         return out
 
     def score_hyps(self, hyps: Dict[str, Dict[str, Sequence[int]]]) -> Dict[str, Dict[str, float]]:

@@ -121,6 +121,17 @@ int pllb_score(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offs
 int pllb_score_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets,
                     int32_t n_hyp, double* out_pll, float* out_token_logp);
 
+/* ---- Sequence-level scoring: replaces the forward of RescoreBert/model.py:13-21 inside
+ * RescoreBert/main.py run_one_epoch (scoring, :232-285): every hypothesis goes through the
+ * encoder ONCE as [CLS] t [SEP] and out[i] = dot(last_hidden_state[i, 0, :], linear_w) +
+ * linear_b.  The handle may be created without MLM head weights (head_w == NULL ...).
+ * linear_w DEVICE float[hidden] (HOST in the _host variant); out_scores float[n_hyp]. */
+int pllb_score_cls(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets,
+                   int32_t n_hyp, const float* linear_w, float linear_b, float* out_scores,
+                   void* stream);
+int pllb_score_cls_host(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets,
+                        int32_t n_hyp, const float* linear_w, float linear_b, float* out_scores);
+
 /* Stage-1 alone, for parity tests against MLM_PLL/preprocess.py:9-30:
  * expands the hypotheses into the packed masked copies.
  * out_ids      DEVICE int32[sum L*(L+2)]  input_ids of every copy, packed

@@ -164,6 +164,57 @@ def pll_golden():
               open(os.path.join(GOLD, "pll_golden.json"), "w"), indent=1)
 
 
+def rescore_bert_golden():
+    """RescoreBert scoring through the reference's own forward (RescoreBert/model.py:13-21) on a
+    transformers.BertModel carrying our encoder weights; BertModel.from_pretrained needs the HF
+    hub, so the module object is assembled by hand and only its forward() comes from the reference."""
+    from transformers import BertConfig, BertModel
+    ref_model = _import_by_path("ref_rescorebert_model", os.path.join(REF, "RescoreBert", "model.py"),
+                                os.path.join(REF, "RescoreBert"))
+    cases = []
+    for name, cfg, seed in (("tiny", synth.BERT_TINY, 31), ("base_chinese", synth.BERT_BASE_CHINESE, 10)):
+        sd = synth.random_init_state_dict(cfg, seed, perturb=(name == "tiny"))
+        g = torch.Generator().manual_seed(seed + 1)
+        lin_w = torch.empty(1, cfg["hidden"]).normal_(0, 0.05, generator=g)
+        lin_b = float(torch.empty(1).normal_(0, 0.5, generator=g))
+        bert = BertModel(BertConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["num_layers"],
+                                    num_attention_heads=cfg["num_heads"], intermediate_size=cfg["intermediate"],
+                                    max_position_embeddings=cfg["max_position"], type_vocab_size=cfg["type_vocab"],
+                                    layer_norm_eps=cfg["ln_eps"], pad_token_id=0, hidden_act="gelu"))
+        enc = {k[len("bert."):]: v for k, v in sd.items() if k.startswith("bert.")}
+        missing, unexpected = bert.load_state_dict(enc, strict=False)
+        assert not unexpected and all("pooler" in m or "position_ids" in m for m in missing), (missing, unexpected)
+        m = object.__new__(ref_model.RescoreBert)
+        torch.nn.Module.__init__(m)
+        m.bert = bert.eval()
+        m.linear = torch.nn.Linear(cfg["hidden"], 1)
+        with torch.no_grad():
+            m.linear.weight.copy_(lin_w)
+            m.linear.bias.fill_(lin_b)
+        nb = synth.make_nbest(4 if name == "tiny" else 2, 4, seed=seed)
+        if name == "tiny":
+            nb.hyps[0][1] = ""
+        tok, off = nb.packed_tokens(cfg["vocab"])
+        lists = [[int(t) for t in tok[off[i]:off[i + 1]]] for i in range(len(off) - 1)]
+        rows = [[101] + t + [102] for t in lists]
+        T = max(len(r) for r in rows)
+        ids = torch.zeros(len(rows), T, dtype=torch.long)
+        am = torch.zeros(len(rows), T, dtype=torch.long)
+        for i, r in enumerate(rows):                      # pad_sequence(batch_first=True), RescoreBert/main.py:59-60
+            ids[i, :len(r)] = torch.tensor(r)
+            am[i, :len(r)] = 1
+        with torch.no_grad():
+            ref_scores = m(ids, am).tolist()
+        mine = pll_oracle.rescore_bert_scores(sd, cfg, lists, lin_w, lin_b)
+        worst = max(abs(a - b) for a, b in zip(ref_scores, mine))
+        print(f"rescorebert[{name}]: {len(rows)} hyps, oracle-vs-reference max |d| = {worst:.2e}")
+        assert worst < 1e-4
+        cases.append(dict(name=name, cfg=cfg, seed=seed, perturb=(name == "tiny"), tokens=lists,
+                          linear_w=lin_w.reshape(-1).tolist(), linear_b=lin_b, scores=ref_scores))
+    json.dump(dict(generator="oracle/make_golden.py", reference="RescoreBert/model.py forward (unmodified)", cases=cases),
+              open(os.path.join(GOLD, "rescorebert_golden.json"), "w"), indent=1)
+
+
 SCORE_IDX = [0, 1, 29, 33, 50, 100]   # grid points whose full score matrix is stored
 
 
@@ -209,3 +260,4 @@ if __name__ == "__main__":
     levenshtein_golden()
     combiner_golden()
     pll_golden()
+    rescore_bert_golden()

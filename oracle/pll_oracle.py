@@ -140,6 +140,28 @@ def score_hyps(sd, cfg, hyps: Dict[str, Dict[str, Sequence[int]]], batch_size: i
     return score_rows(sd, cfg, rows, out, batch_size, token_scores)
 
 
+@torch.no_grad()
+def rescore_bert_scores(sd, cfg, token_lists, linear_w, linear_b, batch_size: int = 32, cls_id=101, sep_id=102):
+    """RescoreBert scoring — RescoreBert/model.py:13-21 (BertModel -> last_hidden_state[:, 0, :] ->
+    Linear(H, 1).squeeze) over batches padded by pad_sequence as in RescoreBert/main.py:31-75.
+    `sd` carries the encoder under the same 'bert.' keys as BertForMaskedLM."""
+    rows = [[cls_id] + list(t) + [sep_id] for t in token_lists]
+    out = []
+    w = torch.as_tensor(linear_w, dtype=torch.float32).reshape(1, -1)
+    b = torch.as_tensor([linear_b], dtype=torch.float32)
+    for s0 in range(0, len(rows), batch_size):
+        batch = rows[s0:s0 + batch_size]
+        T = max(len(r) for r in batch)
+        ids = torch.zeros(len(batch), T, dtype=torch.long)
+        am = torch.zeros(len(batch), T, dtype=torch.long)
+        for i, r in enumerate(batch):
+            ids[i, :len(r)] = torch.tensor(r)
+            am[i, :len(r)] = 1
+        hid = bert_mlm_logits(sd, cfg, ids, am, return_hidden=True)
+        out += F.linear(hid[:, 0, :], w, b).squeeze(dim=-1).tolist()
+    return out
+
+
 def algorithmic_flops(lengths: Sequence[int], cfg: dict) -> float:
     """F(L) = L*[T*NL*(8H^2+4HI) + NL*4*T^2*H + 2H^2 + 2HV]."""
     H, I, NL, V = cfg["hidden"], cfg["intermediate"], cfg["num_layers"], cfg["vocab"]

@@ -338,6 +338,36 @@ def test_config1_100x10_best_against_oracle_acceptance():
     assert abs(cer_g - cer_o) <= 2.0 / sum(len(r) for r in nb.refs)
 
 
+def test_rescorebert_scoring_vs_reference_golden(gold_dir):
+    """Sequence-level scoring ([CLS] -> Linear(H,1)) against the reference's RescoreBert.forward
+    (tests/golden/rescorebert_golden.json) and the live oracle, incl. an empty hypothesis and
+    multi-chunk packing."""
+    import torch
+    from asr_rescoring_b200.RescoreBert.model import RescoreBert
+    gold = json.load(open(os.path.join(gold_dir, "rescorebert_golden.json")))
+    for case in gold["cases"]:
+        sd = synth.random_init_state_dict(case["cfg"], case["seed"], case["perturb"])
+        sd = {k: v for k, v in sd.items() if k.startswith("bert.")}
+        sd["linear.weight"] = torch.tensor(case["linear_w"]).reshape(1, -1)
+        sd["linear.bias"] = torch.tensor([case["linear_b"]])
+        lists = case["tokens"]
+        off = np.zeros(len(lists) + 1, np.int64)
+        np.cumsum([len(t) for t in lists], out=off[1:])
+        tok = np.array([t for l in lists for t in l], np.int32)
+        with RescoreBert(sd, case["cfg"], max_chunk_tokens=1024) as m:
+            got = m.score_packed(tok, off)
+            assert not m.encoder.has_mlm_head
+            from asr_rescoring_b200._lib import PllbError
+            with pytest.raises(PllbError):
+                m.encoder.score_packed(tok, off)          # no MLM head in this checkpoint
+        ref = np.array(case["scores"])
+        # bf16 GEMM operands: the [CLS] state carries ~1e-2 absolute error, the head is a 768-term dot
+        assert np.abs(got - ref).max() < 0.05, np.abs(got - ref).max()
+        full = synth.random_init_state_dict(case["cfg"], case["seed"], case["perturb"])
+        exp = pll_oracle.rescore_bert_scores(full, case["cfg"], lists, case["linear_w"], case["linear_b"])
+        assert np.abs(got - np.array(exp)).max() < 0.05
+
+
 def test_scoring_is_deterministic_and_chunking_invariant():
     cfg = synth.BERT_TINY
     sd = synth.random_init_state_dict(cfg, 4, perturb=True)
