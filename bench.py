@@ -45,6 +45,13 @@ WORKLOADS = {
 }
 
 
+WORKLOAD_DESC = {
+    "c1": "c1: 100 synthetic AISHELL-1-shaped utterances x 10-best, random-init bert-base-chinese, PLL + weight sweep",
+    "c2": "c2: AISHELL-1-test-shaped 7176 utterances x 10-best, random-init bert-base-chinese, PLL + 101-point weight sweep",
+    "c4": "c4: 7176 utterances x 50-best, length 8..64, bert-large-shaped encoder (24L/1024H), PLL + weight sweep",
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,7 +174,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": model, "n_best": n_best, "sample": sample},
+        "config": {"workload": WORKLOAD_DESC[args.workload], "n_best": n_best, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -336,7 +343,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": args.operand_dtype,
             "data": "synthetic",
-            "config": {"workload": args.workload, "model": model, "utterances_per_gpu": N, "n_best": n_best,
+            "config": {"workload": WORKLOAD_DESC[args.workload], "utterances_per_gpu": N, "n_best": n_best,
                        "hyps_per_gpu": n_hyp, "masked_copies_per_gpu": int(lens.sum()),
                        "packed_tokens_per_gpu": int((lens * (lens + 2)).sum()), "weights_grid": W,
                        "chunk_tokens": args.chunk_tokens, "parallelism": f"utterance-sharded x{world}",
