@@ -447,3 +447,15 @@ def test_drop_in_run_one_epoch_matches_oracle_rows():
     for u in exp:
         for h in exp[u]:
             assert abs(got[u][h] - exp[u][h]) <= PLL_TOL
+
+
+def test_drop_in_cli_end_to_end():
+    """MLM_PLL/main.py --config score.yaml and rescore.py --config rescore.yaml as processes, on
+    synthetic hyps_text / hyps_score / ref_text files, checked against the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "e2e_dropin.py")], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "rescore.log matches the oracle" in out.stdout
