@@ -33,7 +33,7 @@ if _PKG_PARENT not in sys.path:
 
 from asr_rescoring_b200 import shard, synth  # noqa: E402
 from asr_rescoring_b200.engine import PllScorer  # noqa: E402
-from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer  # noqa: E402
+from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer, encode_batch  # noqa: E402
 from asr_rescoring_b200.util.arg_parser import ArgParser  # noqa: E402
 from asr_rescoring_b200.util.saving import json_saving  # noqa: E402
 
@@ -141,8 +141,16 @@ def load_split(path: str, num_of_data: int, config) -> Tuple[Optional[list], Dic
         for i, (u, h) in enumerate(zip(data["utt_id"], data["hyp_id"])):
             hyps.setdefault(u, {})[h] = tok[off[i]:off[i + 1]]
         return None, hyps
-    tk = _tokenizer(config)                          # hyps_text.json
-    return None, {u: {h: tk.encode(s) for h, s in hs.items()} for u, hs in data.items()}
+    tk = _tokenizer(config)                          # hyps_text.json: one batched tokenizer call
+    ids, off = encode_batch(tk, [s for hs in data.values() for s in hs.values()])
+    ids, off = ids.tolist(), off.tolist()
+    hyps, i = {}, 0
+    for u, hs in data.items():
+        hyps[u] = {}
+        for h in hs:
+            hyps[u][h] = ids[off[i]:off[i + 1]]
+            i += 1
+    return None, hyps
 
 
 def skeleton_from_rows(rows: list) -> dict:

@@ -729,6 +729,55 @@ int pllb_levenshtein(const int32_t* ref_cp, const int64_t* ref_off, const int32_
   return launch_levenshtein(ref_cp, ref_off, hyp_cp, hyp_off, pair_ref, n_pairs, max_len, out_dist, (cudaStream_t)stream);
 }
 
+int pllb_tokenize_host(const int32_t* table, int32_t table_size, const int32_t* cp, const int64_t* cp_off, int32_t n_hyp,
+                       int32_t* out_ids, int64_t* out_off, uint8_t* needs_host) {
+  RC(check_device());
+  if (n_hyp < 0 || table_size <= 0) return fail(PLLB_ERR_INVALID, "pllb_tokenize_host: bad size");
+  if (!table || !cp_off || !out_off || (n_hyp > 0 && !needs_host)) return fail(PLLB_ERR_INVALID, "pllb_tokenize_host: null argument");
+  out_off[0] = 0;
+  if (n_hyp == 0) return PLLB_OK;
+  const int64_t n_cp = cp_off[n_hyp] - cp_off[0];
+  if (n_cp < 0 || (n_cp > 0 && (!cp || !out_ids))) return fail(PLLB_ERR_INVALID, "pllb_tokenize_host: bad offsets");
+  for (int32_t i = 0; i < n_hyp; ++i)
+    if (cp_off[i + 1] < cp_off[i]) return fail(PLLB_ERR_INVALID, "pllb_tokenize_host: offsets not ascending");
+  const int64_t b0 = align_up(4 * (int64_t)table_size, 256), b1 = align_up(4 * std::max<int64_t>(n_cp, 1), 256),
+                b2 = align_up(8 * (int64_t)(n_hyp + 1), 256), b3 = align_up(4 * (int64_t)n_hyp, 256),
+                b4 = align_up((int64_t)n_hyp, 256), b5 = b2, b6 = b1;
+  uint8_t* base = nullptr;
+  RC(get_scratch(b0 + b1 + b2 + b3 + b4 + b5 + b6, &base));
+  int32_t* d_table = (int32_t*)base;
+  int32_t* d_cp = (int32_t*)(base + b0);
+  int64_t* d_off = (int64_t*)(base + b0 + b1);
+  int32_t* d_cnt = (int32_t*)(base + b0 + b1 + b2);
+  uint8_t* d_flag = base + b0 + b1 + b2 + b3;
+  int64_t* d_ooff = (int64_t*)(base + b0 + b1 + b2 + b3 + b4);
+  int32_t* d_ids = (int32_t*)(base + b0 + b1 + b2 + b3 + b4 + b5);
+  cudaStream_t s = 0;
+  std::vector<int64_t> rel(n_hyp + 1);                        // offsets relative to the first code point
+  for (int32_t i = 0; i <= n_hyp; ++i) rel[i] = cp_off[i] - cp_off[0];
+  std::vector<int32_t> cnt(n_hyp);
+  int rc = PLLB_OK;
+  cudaError_t e = cudaMemcpyAsync(d_table, table, 4 * (int64_t)table_size, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && n_cp > 0) e = cudaMemcpyAsync(d_cp, cp + cp_off[0], 4 * n_cp, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, rel.data(), 8 * (int64_t)(n_hyp + 1), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) rc = launch_tokenize_count(d_table, table_size, d_cp, d_off, n_hyp, d_cnt, d_flag, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaMemcpyAsync(cnt.data(), d_cnt, 4 * (int64_t)n_hyp, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaMemcpyAsync(needs_host, d_flag, n_hyp, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaStreamSynchronize(s);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("pllb_tokenize_host: ") + cudaGetErrorString(e));
+  for (int32_t i = 0; i < n_hyp; ++i) out_off[i + 1] = out_off[i] + cnt[i];
+  const int64_t n_out = out_off[n_hyp];
+  if (n_out == 0) return PLLB_OK;
+  e = cudaMemcpyAsync(d_ooff, out_off, 8 * (int64_t)(n_hyp + 1), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) rc = launch_tokenize_write(d_table, table_size, d_cp, d_off, n_hyp, d_flag, d_ooff, d_ids, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaMemcpyAsync(out_ids, d_ids, 4 * n_out, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && rc == PLLB_OK) e = cudaStreamSynchronize(s);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("pllb_tokenize_host: ") + cudaGetErrorString(e));
+  return PLLB_OK;
+}
+
 int pllb_levenshtein_host(const int32_t* ref_cp, const int64_t* ref_off, int32_t n_ref, const int32_t* hyp_cp,
                           const int64_t* hyp_off, const int32_t* pair_ref, int32_t n_pairs, int32_t* out_dist) {
   RC(check_device());

@@ -124,6 +124,10 @@ int launch_rescore_sweep(const double* am, const double* lm, const int64_t* len,
                          int64_t* out_edit_sum, cudaStream_t s);
 int launch_rescore_scores(const double* am, const double* lm, const int64_t* len, int32_t N, int32_t n_best,
                           double weight, int32_t variant, double* out, cudaStream_t s);
+int launch_tokenize_count(const int32_t* table, int table_size, const int32_t* cp, const int64_t* cp_off, int32_t n_hyp,
+                          int32_t* counts, uint8_t* needs_host, cudaStream_t s);
+int launch_tokenize_write(const int32_t* table, int table_size, const int32_t* cp, const int64_t* cp_off, int32_t n_hyp,
+                          const uint8_t* needs_host, const int64_t* out_off, int32_t* out_ids, cudaStream_t s);
 int launch_levenshtein(const int32_t* ref_cp, const int64_t* ref_off, const int32_t* hyp_cp, const int64_t* hyp_off,
                        const int32_t* pair_ref, int32_t n_pairs, int32_t max_len, int32_t* out, cudaStream_t s);
 

@@ -911,4 +911,70 @@ int launch_f32_to_bf16(const float* src, void* dst, int64_t n, bool fp16, cudaSt
   return PLLB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Text front end: code points -> wordpiece ids for hypotheses made of
+// CJK ideographs, punctuation and whitespace — BertTokenizer.tokenize + convert_tokens_to_ids at
+// MLM_PLL/preprocess.py:10,16-27 (BasicTokenizer makes every such character its own token, so
+// the mapping is a table lookup).  table[cp] >= 0: id; -1 whitespace (dropped); -2 removed
+// (control, U+0000, U+FFFD); -3 part of a word run -> the whole hypothesis is flagged for the
+// host wordpiece tokenizer and gets 0 tokens here.  One warp per hypothesis.
+__device__ __forceinline__ int tok_lookup(const int32_t* __restrict__ table, int table_size, int32_t c) {
+  return (c >= 0 && c < table_size) ? __ldg(table + c) : -3;
+}
+
+__global__ void tokenize_count_kernel(const int32_t* __restrict__ table, int table_size, const int32_t* __restrict__ cp,
+                                      const int64_t* __restrict__ cp_off, int32_t n_hyp, int32_t* __restrict__ counts,
+                                      uint8_t* __restrict__ needs_host) {
+  const int h = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (h >= n_hyp) return;
+  const int64_t b = cp_off[h], e = cp_off[h + 1];
+  int n = 0, word = 0;
+  for (int64_t i = b + lane; i < e; i += 32) {
+    const int t = tok_lookup(table, table_size, cp[i]);
+    n += t >= 0;
+    word |= t == -3;
+  }
+  n = __reduce_add_sync(0xffffffffu, n);
+  word = __any_sync(0xffffffffu, word);
+  if (lane == 0) {
+    counts[h] = word ? 0 : n;
+    needs_host[h] = (uint8_t)word;
+  }
+}
+
+__global__ void tokenize_write_kernel(const int32_t* __restrict__ table, int table_size, const int32_t* __restrict__ cp,
+                                      const int64_t* __restrict__ cp_off, int32_t n_hyp,
+                                      const uint8_t* __restrict__ needs_host, const int64_t* __restrict__ out_off,
+                                      int32_t* __restrict__ out_ids) {
+  const int h = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (h >= n_hyp || needs_host[h]) return;
+  const int64_t b = cp_off[h], e = cp_off[h + 1];
+  int64_t o = out_off[h];
+  for (int64_t i0 = b; i0 < e; i0 += 32) {                    // warp-uniform trip count
+    const int64_t i = i0 + lane;
+    const int t = i < e ? tok_lookup(table, table_size, cp[i]) : -1;
+    const unsigned keep = __ballot_sync(0xffffffffu, t >= 0);
+    if (t >= 0) out_ids[o + __popc(keep & ((1u << lane) - 1u))] = t;
+    o += __popc(keep);
+  }
+}
+
+int launch_tokenize_count(const int32_t* table, int table_size, const int32_t* cp, const int64_t* cp_off, int32_t n_hyp,
+                          int32_t* counts, uint8_t* needs_host, cudaStream_t s) {
+  if (n_hyp <= 0) return PLLB_OK;
+  tokenize_count_kernel<<<(unsigned)ceil_div((int64_t)n_hyp, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(
+      table, table_size, cp, cp_off, n_hyp, counts, needs_host);
+  PLLB_LAUNCH_CHECK("tokenize_count_kernel");
+  return PLLB_OK;
+}
+
+int launch_tokenize_write(const int32_t* table, int table_size, const int32_t* cp, const int64_t* cp_off, int32_t n_hyp,
+                          const uint8_t* needs_host, const int64_t* out_off, int32_t* out_ids, cudaStream_t s) {
+  if (n_hyp <= 0) return PLLB_OK;
+  tokenize_write_kernel<<<(unsigned)ceil_div((int64_t)n_hyp, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(
+      table, table_size, cp, cp_off, n_hyp, needs_host, out_off, out_ids);
+  PLLB_LAUNCH_CHECK("tokenize_write_kernel");
+  return PLLB_OK;
+}
+
 }  // namespace pllb

@@ -231,6 +231,22 @@ def pack_strings(strings: Sequence[str]):
     return cp, off
 
 
+def tokenize_packed(table: np.ndarray, cp: np.ndarray, cp_off: np.ndarray):
+    """pllb_tokenize_host: packed code points -> (ids int32, offsets int64[n+1], needs_host uint8[n])."""
+    lib = _lib.load()
+    _lib.require_device()
+    table = np.ascontiguousarray(table, np.int32)
+    cp = np.ascontiguousarray(cp, np.int32)
+    cp_off = np.ascontiguousarray(cp_off, np.int64)
+    n = len(cp_off) - 1
+    ids = np.zeros(max(int(cp_off[-1] - cp_off[0]), 1), np.int32)
+    off = np.zeros(n + 1, np.int64)
+    flag = np.zeros(max(n, 1), np.uint8)
+    check(lib.pllb_tokenize_host(_np_ptr(table), len(table), _np_ptr(cp), _np_ptr(cp_off), n, _np_ptr(ids), _np_ptr(off),
+                                 _np_ptr(flag)))
+    return ids[:int(off[-1])], off, flag[:n]
+
+
 def levenshtein_packed(ref_cp, ref_off, hyp_cp, hyp_off, pair_ref) -> np.ndarray:
     """Edit distances of (ref[pair_ref[i]], hyp[i]) pairs on the GPU (host arrays in/out)."""
     lib = _lib.load()

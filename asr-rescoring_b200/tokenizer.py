@@ -15,9 +15,14 @@ and is not available offline, so two modes exist:
 from __future__ import annotations
 
 import unicodedata
-from typing import Dict, List
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
 
 from .synth import UNK_ID, synthetic_token_id
+
+TABLE_SIZE = 0x30000             # covers the BMP and every CJK extension block _is_cjk knows
+TOK_SPACE, TOK_REMOVED, TOK_WORD = -1, -2, -3      # include/pllb.h PLLB_TOK_*
 
 
 def _is_cjk(cp: int) -> bool:
@@ -52,6 +57,14 @@ class SyntheticCharTokenizer:
 
     def encode(self, text: str) -> List[int]:
         return self.convert_tokens_to_ids(self.tokenize(text))
+
+    def char_table(self) -> np.ndarray:
+        """Every code point is its own token (nothing is dropped)."""
+        if getattr(self, "_table", None) is None:
+            cp = np.arange(TABLE_SIZE, dtype=np.int64)
+            rank = np.where((cp >= 0x4E00) & (cp < 0x4E00 + 20000), ((cp - 0x4E00) * 17143) % 20000, cp)
+            self._table = (670 + rank % 7322).astype(np.int32)
+        return self._table
 
 
 class BertCharTokenizer:
@@ -125,3 +138,59 @@ class BertCharTokenizer:
 
     def encode(self, text: str) -> List[int]:
         return self.convert_tokens_to_ids(self.tokenize(text))
+
+    def char_table(self) -> np.ndarray:
+        """int32[TABLE_SIZE] for pllb_tokenize_host: the id of every character that BasicTokenizer
+        always isolates as its own token (CJK ideographs, punctuation), TOK_SPACE / TOK_REMOVED for
+        characters that emit nothing, TOK_WORD for everything whose tokenisation depends on its
+        neighbours (those hypotheses go through ``encode``)."""
+        if getattr(self, "_table", None) is not None:
+            return self._table
+        unk = self.vocab.get(self.unk_token, UNK_ID)
+        table = np.full(TABLE_SIZE, TOK_WORD, np.int32)
+        probe = next((chr(c) for c in range(0x4E00, 0x9FFF) if chr(c) in self.vocab), None)
+        for cp in range(TABLE_SIZE):
+            if 0xD800 <= cp <= 0xDFFF:
+                continue
+            ch = chr(cp)
+            if cp == 0 or cp == 0xFFFD or _is_control(ch):
+                table[cp] = TOK_REMOVED
+            elif _is_whitespace(ch):
+                table[cp] = TOK_SPACE
+            elif _is_cjk(cp):
+                n = unicodedata.normalize("NFC", ch)
+                if len(n) == 1 and _is_cjk(ord(n)):
+                    table[cp] = self.vocab.get(n, unk)
+            elif _is_punct(ch):
+                # context-free only if it stays one token between two ideographs
+                one = self.encode(ch)
+                if len(one) == 1 and (probe is None or
+                                      self.encode(probe + ch + probe) == [self.vocab[probe], one[0], self.vocab[probe]]):
+                    table[cp] = one[0]
+        self._table = table
+        return table
+
+
+def encode_batch(tokenizer, strings: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
+    """All strings -> (ids int32[sum], offsets int64[n+1]): one pllb_tokenize_host call for the
+    CJK/punctuation hypotheses, ``tokenizer.encode`` on the host for the flagged rest
+    (replaces the per-sentence tokenizer calls of MLM_PLL/preprocess.py:10,16-27)."""
+    from . import engine
+    n = len(strings)
+    cp, cp_off = engine.pack_strings(strings)
+    ids, off, flag = engine.tokenize_packed(tokenizer.char_table(), cp, cp_off)
+    if not flag.any():
+        return ids, off
+    lens = np.diff(off)
+    host = {int(i): np.asarray(tokenizer.encode(strings[int(i)]), np.int32) for i in np.nonzero(flag)[0]}
+    for i, v in host.items():
+        lens[i] = len(v)
+    new_off = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    out = np.empty(int(new_off[-1]), np.int32)
+    keep = flag == 0
+    shift = np.repeat(new_off[:-1][keep] - off[:-1][keep], np.diff(off)[keep])
+    out[np.arange(len(ids), dtype=np.int64) + shift] = ids
+    for i, v in host.items():
+        out[new_off[i]:new_off[i + 1]] = v
+    return out, new_off

@@ -167,6 +167,25 @@ int pllb_debug_gemm_simt(const uint16_t* A, const uint16_t* W, const float* bias
 int pllb_debug_hidden(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets,
                       int32_t n_hyp, int32_t upto_layer, float* out_hidden, void* stream);
 
+/* ---- Text front end: replaces BertTokenizer.tokenize + convert_tokens_to_ids
+ * (MLM_PLL/preprocess.py:10,16-27,34) for hypotheses made of CJK ideographs,
+ * punctuation and whitespace, where BERT's BasicTokenizer makes every character
+ * its own token.  Strings are packed Unicode code points (HOST arrays).
+ * table int32[table_size], indexed by code point:
+ *   >= 0              wordpiece id of the character as a token ([UNK] if not in the vocab)
+ *   PLLB_TOK_SPACE    whitespace: separates, emits nothing
+ *   PLLB_TOK_REMOVED  control character, U+0000, U+FFFD: removed
+ *   PLLB_TOK_WORD     part of a word run (Latin, digits, kana, marks ...): the hypothesis
+ *                     needs the host wordpiece tokenizer; needs_host[h] = 1 and it gets
+ *                     0 tokens here.  Code points >= table_size count as PLLB_TOK_WORD.
+ * out_ids: capacity cp_off[n_hyp]; out_off int64[n_hyp+1]; needs_host uint8[n_hyp]. */
+#define PLLB_TOK_SPACE (-1)
+#define PLLB_TOK_REMOVED (-2)
+#define PLLB_TOK_WORD (-3)
+int pllb_tokenize_host(const int32_t* table, int32_t table_size, const int32_t* cp,
+                       const int64_t* cp_off, int32_t n_hyp, int32_t* out_ids,
+                       int64_t* out_off, uint8_t* needs_host);
+
 /* ---- Levenshtein: replaces jiwer.cer's per-pair edit distance at
  * rescore.py:40,118 (and espnet_data/preprocess/main.py:59-60).
  * Strings are packed arrays of Unicode code points.

@@ -459,3 +459,40 @@ def test_drop_in_cli_end_to_end():
                          timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert "rescore.log matches the oracle" in out.stdout
+
+
+def test_text_front_end_matches_the_host_tokenizer(tmp_path):
+    """pllb_tokenize_host (+ host path for flagged hypotheses) == BertTokenizer-style encode, per string."""
+    from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer, encode_batch
+    nb = synth.make_nbest(300, 10, seed=21)
+    chars = sorted({c for r in nb.refs for c in r})
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "a", "ab", "##c", "##d", "hello", "1", "##2", ",", "。", "，", "?"] + chars[::2]
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    strings = [h for hs in nb.hyps for h in hs]
+    rng = np.random.default_rng(3)
+    extra = ["", " ", "你好abc", "hello，世界", "abcd 12", "\x00" + strings[0] + "\ufffd", strings[1] + "\u3000" + strings[2],
+             chr(0xF900) + strings[3], "。，?" + strings[4], chr(0x20000) + chr(0x2A700), "a\u0301" + strings[5], "あいう"]
+    for i in rng.integers(0, len(strings), 40):                       # sprinkle whitespace / punctuation / Latin
+        sidx = int(i)
+        strings[sidx] = strings[sidx][:2] + str(rng.choice([" ", "，", "a", "\t", "12", "?"])) + strings[sidx][2:]
+    strings += extra
+    for tk in (BertCharTokenizer(str(vp)), SyntheticCharTokenizer()):
+        ids, off = encode_batch(tk, strings)
+        assert off[0] == 0 and len(off) == len(strings) + 1 and off[-1] == len(ids)
+        for i, s_ in enumerate(strings):
+            assert ids[off[i]:off[i + 1]].tolist() == tk.encode(s_), (type(tk).__name__, repr(s_))
+    try:
+        from transformers import BertTokenizer
+        hf = BertTokenizer(str(vp))
+    except Exception:
+        hf = None
+    if hf is not None:
+        ids, off = encode_batch(BertCharTokenizer(str(vp)), strings)
+        for i, s_ in enumerate(strings):
+            assert ids[off[i]:off[i + 1]].tolist() == hf.convert_tokens_to_ids(hf.tokenize(s_)), repr(s_)
+    # empty batch and all-flagged batch
+    ids, off = encode_batch(SyntheticCharTokenizer(), [])
+    assert len(ids) == 0 and off.tolist() == [0]
+    ids, off = encode_batch(BertCharTokenizer(str(vp)), ["abc", "hello 12"])
+    assert ids.tolist() == BertCharTokenizer(str(vp)).encode("abc") + BertCharTokenizer(str(vp)).encode("hello 12")

@@ -154,3 +154,38 @@ def test_gloo_world_size_2_gather_and_reduce(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["ok"] and res["counts"] == [148, sum(range(148))]
+
+
+def _table_lookup_reference(table, text):
+    """numpy restatement of pllb_tokenize_host for one string: ids, or None if flagged."""
+    cps = [ord(c) for c in text]
+    t = [int(table[c]) if c < len(table) else -3 for c in cps]
+    if any(x == -3 for x in t):
+        return None
+    return [x for x in t if x >= 0]
+
+
+def test_char_table_agrees_with_the_wordpiece_tokenizer(tmp_path):
+    from asr_rescoring_b200.tokenizer import TOK_REMOVED, TOK_SPACE, TOK_WORD
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "你", "好", "嗎", "豈", "a", "ab", "##c", "1", ",", "。", "，", "!", "$"]
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    tk = BertCharTokenizer(str(vp))
+    table = tk.char_table()
+    assert table[ord("你")] == 5 and table[ord("龘")] == 1            # in vocab / [UNK]
+    assert table[0xF900] == vocab.index("豈")                         # compatibility ideograph -> NFC form
+    assert table[ord(" ")] == TOK_SPACE and table[0x3000] == TOK_SPACE
+    assert table[0] == TOK_REMOVED and table[0xFFFD] == TOK_REMOVED and table[0x200B] == TOK_REMOVED
+    assert table[ord("a")] == TOK_WORD and table[ord("1")] == TOK_WORD and table[0x0301] == TOK_WORD
+    assert table[ord("あ")] == TOK_WORD                               # kana is not split by BasicTokenizer
+    assert table[ord(",")] == vocab.index(",") and table[ord("?")] == 1
+    rng = np.random.default_rng(5)
+    alphabet = list("你好嗎豈龘，。,!?$ \t\u3000\x00\ufffd\u200b") + [chr(0xF900), chr(0x20000)]
+    for _ in range(300):
+        text = "".join(rng.choice(alphabet, size=int(rng.integers(0, 12))))
+        assert _table_lookup_reference(table, text) == tk.encode(text), repr(text)
+    assert _table_lookup_reference(table, "你好abc") is None
+    syn = SyntheticCharTokenizer()
+    st = syn.char_table()
+    for text in ("你好嗎", "abc 1", "龘\u3000x"):
+        assert _table_lookup_reference(st, text) == syn.encode(text)
