@@ -224,10 +224,12 @@ class PllScorer:
 
 # ---------------------------------------------------------------------- stage 4
 def pack_strings(strings: Sequence[str]):
+    """Strings -> (code points int32[sum len], offsets int64[n+1]); len = Python code points."""
     off = np.zeros(len(strings) + 1, np.int64)
     if len(strings):
-        np.cumsum([len(s) for s in strings], out=off[1:])
-    cp = np.fromiter((ord(c) for s in strings for c in s), np.int32, int(off[-1]))
+        np.cumsum(np.fromiter(map(len, strings), np.int64, len(strings)), out=off[1:])
+    cp = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), np.int32)
+    assert len(cp) == off[-1]
     return cp, off
 
 
