@@ -228,7 +228,7 @@ def pack_strings(strings: Sequence[str]):
     off = np.zeros(len(strings) + 1, np.int64)
     if len(strings):
         np.cumsum(np.fromiter(map(len, strings), np.int64, len(strings)), out=off[1:])
-    cp = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), np.int32)
+    cp = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), np.int32).copy()
     assert len(cp) == off[-1]
     return cp, off
 

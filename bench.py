@@ -170,7 +170,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = n / (ms / 1e3)
     sample = f"first {n} hypotheses ({copies} masked copies) of workload {args.workload}, batch 32, fp32, per step"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -178,11 +178,30 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep fd 1 for the JSON line only: everything else that writes to stdout during the run
+    (NCCL's version banner, library chatter) is sent to stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.operand_dtype is None:
         args.operand_dtype = "fp16" if args.workload == "c4" else "bf16"
     if args.impl == "reference":
@@ -379,8 +398,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        sys.stderr.flush()
-        print(json.dumps(out), flush=True)     # the JSON line is the last thing rank 0 prints
+        _emit(out)                             # the JSON line is the only thing on stdout
 
 
 if __name__ == "__main__":
