@@ -524,12 +524,13 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
         }
       }
       float bm[2] = {-INFINITY, -INFINITY};
+      const bool tail = k0 + 16 > T;                      // warp-uniform: only the last key block has padding keys
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int key = k0 + 8 * j + 2 * cq + (e & 1);
-          s[j][e] = key < T ? s[j][e] * kScaleLog2 : -INFINITY;
+          s[j][e] = (!tail || key < T) ? s[j][e] * kScaleLog2 : -INFINITY;
           bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
         }
       }
@@ -576,13 +577,27 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
       l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
     }
     const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
-    const int q0 = m0 + g, q1 = m0 + g + 8;
+    // The Q rows of this block live in qf now: reuse them to transpose the context block so that
+    // it leaves as 16-byte row-contiguous stores (4-byte fragment stores cost 8x the L1 wavefronts).
+    __syncwarp();
+    {
+      const uint32_t st0 = q_addr + (uint32_t)((m0 + g) * ATT_VROW + 2 * cq) * 2, st1 = st0 + 8 * ATT_VROW * 2;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (q0 < T)
-        *reinterpret_cast<uint32_t*>(ob + (size_t)q0 * H + 8 * n + 2 * cq) = pack16<FP16>(o[n][0] * inv0, o[n][1] * inv0);
-      if (q1 < T)
-        *reinterpret_cast<uint32_t*>(ob + (size_t)q1 * H + 8 * n + 2 * cq) = pack16<FP16>(o[n][2] * inv1, o[n][3] * inv1);
+      for (int n = 0; n < 8; ++n) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(st0 + 16 * n), "r"(pack16<FP16>(o[n][0] * inv0, o[n][1] * inv0)) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(st1 + 16 * n), "r"(pack16<FP16>(o[n][2] * inv1, o[n][3] * inv1)) : "memory");
+      }
+    }
+    __syncwarp();
+    {
+      const int r_off = lane >> 3, ch = lane & 7;
+#pragma unroll
+      for (int rr = 0; rr < 16; rr += 4) {
+        const int q = m0 + rr + r_off;
+        if (q < T)
+          *reinterpret_cast<uint4*>(ob + (size_t)q * H + ch * 8) =
+              *reinterpret_cast<const uint4*>(sm + q * ATT_VROW + ch * 8);
+      }
     }
   }
 }
