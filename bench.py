@@ -92,7 +92,7 @@ class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
@@ -118,8 +118,18 @@ class ClockSampler(threading.Thread):
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+
+        def _num(col):
+            vals = []
+            for smp in self.samples:
+                try:
+                    vals.append(float(smp[col]))
+                except (IndexError, ValueError):
+                    pass
+            return float(np.median(vals)) if vals else None
+
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "power_w": _num(6), "power_limit_w": _num(7)}
 
 
 def cpu_port_hyps_per_s(cfg, sd, tok, off, n_hyps, threads=None):
