@@ -83,6 +83,8 @@ struct pllb_context {
   int32_t* meta_dev = nullptr;
   int32_t* meta_host = nullptr;     // pinned
   int64_t meta_cap = 0;
+  cudaEvent_t ev_meta = nullptr;    // recorded after the H2D copy of meta_host: the next call waits on it before refilling
+  bool meta_pending = false;
   // scratch for the _host entry points
   void* io_dev = nullptr;
   int64_t io_cap = 0;
@@ -260,6 +262,26 @@ int ensure_meta(pllb_context* c, int64_t need, cudaStream_t s) {
   return PLLB_OK;
 }
 
+// Calls are asynchronous: the previous call's copy out of the pinned metadata buffer may still be
+// queued behind its predecessor's kernels.  meta_acquire waits for that copy (not for the
+// kernels) before the host refills the buffer; meta_upload copies and records the event.
+int meta_acquire(pllb_context* c) {
+  if (c->meta_pending) {
+    PLLB_CUDA(cudaEventSynchronize(c->ev_meta));
+    c->meta_pending = false;
+  }
+  return PLLB_OK;
+}
+
+int meta_upload(pllb_context* c, int64_t count, cudaStream_t s) {
+  if (count <= 0) return PLLB_OK;
+  PLLB_CUDA(cudaMemcpyAsync(c->meta_dev, c->meta_host, sizeof(int32_t) * count, cudaMemcpyHostToDevice, s));
+  if (!c->ev_meta) PLLB_CUDA(cudaEventCreateWithFlags(&c->ev_meta, cudaEventDisableTiming));
+  PLLB_CUDA(cudaEventRecord(c->ev_meta, s));
+  c->meta_pending = true;
+  return PLLB_OK;
+}
+
 // Plans chunks on the host (offsets are control metadata), uploads the metadata once and
 // enqueues every chunk on `s` without synchronising.
 // cls != nullptr: sequence-level scoring ([CLS] t [SEP], one pass per hypothesis, Linear(H,1)
@@ -304,6 +326,7 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
     meta_need += 3 * (int64_t)(ch.n_hyp + 1);
   }
   RC(ensure_meta(c, meta_need, s));
+  RC(meta_acquire(c));
   for (const auto& ch : chunks) {
     int32_t* tok_off = c->meta_host + ch.meta_off;
     int32_t* copy_base = tok_off + (ch.n_hyp + 1);
@@ -317,8 +340,7 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
       }
     }
   }
-  if (meta_need > 0)
-    PLLB_CUDA(cudaMemcpyAsync(c->meta_dev, c->meta_host, sizeof(int32_t) * meta_need, cudaMemcpyHostToDevice, s));
+  RC(meta_upload(c, meta_need, s));
   if (c->timing) {
     if (!c->ev_begin) { PLLB_CUDA(cudaEventCreate(&c->ev_begin)); PLLB_CUDA(cudaEventCreate(&c->ev_end)); }
     PLLB_CUDA(cudaEventRecord(c->ev_begin, s));
@@ -531,6 +553,7 @@ int pllb_destroy(pllb_handle h) {
   for (void* p : h->owned) cudaFree(p);
   if (h->meta_dev) cudaFree(h->meta_dev);
   if (h->meta_host) cudaFreeHost(h->meta_host);
+  if (h->ev_meta) cudaEventDestroy(h->ev_meta);
   if (h->io_dev) cudaFree(h->io_dev);
   for (auto& t : h->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   if (h->ev_begin) { cudaEventDestroy(h->ev_begin); cudaEventDestroy(h->ev_end); }
@@ -636,6 +659,7 @@ int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, in
   if (copies > h->cap_copies || rows > INT32_MAX || n_hyp > h->cap_hyps)
     return fail(PLLB_ERR_OOM, "pllb_expand: input exceeds one chunk");
   RC(ensure_meta(h, 3 * (int64_t)(n_hyp + 1), s));
+  RC(meta_acquire(h));
   int32_t* tok_off = h->meta_host;
   int32_t* copy_base = tok_off + (n_hyp + 1);
   int32_t* row_base = copy_base + (n_hyp + 1);
@@ -644,7 +668,7 @@ int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, in
     tok_off[i] = (int32_t)t; copy_base[i] = (int32_t)cb; row_base[i] = (int32_t)rb;
     if (i < n_hyp) { const int64_t L = off[i + 1] - off[i]; t += L; cb += L; rb += L * (L + 2); }
   }
-  PLLB_CUDA(cudaMemcpyAsync(h->meta_dev, h->meta_host, sizeof(int32_t) * 3 * (n_hyp + 1), cudaMemcpyHostToDevice, s));
+  RC(meta_upload(h, 3 * (int64_t)(n_hyp + 1), s));
   const int32_t* d_tok_off = h->meta_dev;
   hyp_tokens += off[0];
   RC(launch_expand_plan(hyp_tokens, d_tok_off, d_tok_off + (n_hyp + 1), d_tok_off + 2 * (n_hyp + 1), n_hyp, h->d.vocab,

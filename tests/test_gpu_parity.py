@@ -496,3 +496,27 @@ def test_text_front_end_matches_the_host_tokenizer(tmp_path):
     assert len(ids) == 0 and off.tolist() == [0]
     ids, off = encode_batch(BertCharTokenizer(str(vp)), ["abc", "hello 12"])
     assert ids.tolist() == BertCharTokenizer(str(vp)).encode("abc") + BertCharTokenizer(str(vp)).encode("hello 12")
+
+
+def test_back_to_back_async_calls_keep_their_own_metadata():
+    """pllb_score is asynchronous on the caller's stream; three calls with different hypothesis
+    sets issued without any synchronisation must each score their own input (the host-side
+    metadata staging buffer is reused across calls)."""
+    import torch
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 4)
+    nbs = [synth.make_nbest(400, 10, seed=31), synth.make_nbest(30, 10, seed=32), synth.make_nbest(30, 10, seed=33)]
+    packed = []
+    for nb in nbs:
+        tok, off = nb.packed_tokens()
+        packed.append((torch.from_numpy(np.ascontiguousarray(tok)).cuda(), off))
+    with engine.PllScorer(sd, cfg, max_chunk_tokens=8192) as sc:
+        alone = []
+        for tok, off in packed:
+            alone.append(sc.score_device(tok, off).clone())
+            torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        outs = [sc.score_device(tok, off) for tok, off in packed]      # no sync in between
+        torch.cuda.synchronize()
+        for a, b in zip(alone, outs):
+            assert torch.equal(a, b)
