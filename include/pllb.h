@@ -113,7 +113,11 @@ int64_t pllb_workspace_bytes(pllb_handle h);
  *                                     log_softmax(logits[mask_pos])[token]
  *                                     (a hypothesis with L == 0 gets 0.0)
  * out_token_logp DEVICE float[hyp_offsets[n_hyp]] or NULL; the individual terms
- * Asynchronous on `stream`. */
+ * Asynchronous on `stream`: hyp_offsets is consumed before the call returns, the
+ * device buffers when the stream reaches the work.  A handle owns ONE workspace:
+ * use it from one host thread and issue its calls on one stream (calls may be queued
+ * back to back without synchronising; work on different streams must be ordered by
+ * the caller). */
 int pllb_score(pllb_handle h, const int32_t* hyp_tokens, const int64_t* hyp_offsets,
                int32_t n_hyp, double* out_pll, float* out_token_logp, void* stream);
 
