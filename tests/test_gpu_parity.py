@@ -520,3 +520,22 @@ def test_back_to_back_async_calls_keep_their_own_metadata():
         torch.cuda.synchronize()
         for a, b in zip(alone, outs):
             assert torch.equal(a, b)
+
+
+def test_degenerate_batches():
+    """No hypotheses, only empty hypotheses, a single one-token hypothesis, and stage 4 with N = 0."""
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 6)
+    with engine.PllScorer(sd, cfg) as sc:
+        assert sc.score_packed(np.zeros(0, np.int32), np.zeros(1, np.int64)).shape == (0,)
+        out = sc.score_packed(np.zeros(0, np.int32), np.zeros(4, np.int64))
+        assert out.tolist() == [0.0, 0.0, 0.0]
+        one, terms = sc.score_packed(np.array([700], np.int32), np.array([0, 1], np.int64), return_token_logp=True)
+        exp = pll_oracle.score_hyps(sd, cfg, {"u": {"hyp_1": [700]}})["u"]["hyp_1"]
+        assert abs(one[0] - exp) <= PLL_TOL and abs(float(terms[0]) - one[0]) < 1e-6
+        mixed = sc.score_packed(np.array([700], np.int32), np.array([0, 0, 1, 1], np.int64))
+        assert mixed[0] == 0.0 and mixed[2] == 0.0 and mixed[1] == one[0]
+        assert sc.score_cls_packed(np.zeros(0, np.int32), np.zeros(1, np.int64), np.zeros(cfg["hidden"], np.float32), 0.0).shape == (0,)
+    assert engine.levenshtein([], []).shape == (0,)
+    assert engine.levenshtein([""], [""]).tolist() == [0]
+    assert engine.levenshtein(["abc"], [""]).tolist() == [3]
