@@ -15,7 +15,8 @@ ensure_ascii=False).  Differences, each deliberate (SURVEY.md §8a "quirks"):
   ``hyps_text.json`` ({utt: {hyp: str}}, tokenised here) or the compact packed JSON that
   our ``preprocess.py`` writes — the O(sum L^2) row list is never needed;
 * optional keys (absent from the reference YAMLs, all defaulted): ``model.vocab_path``,
-  ``model.random_init_seed``, ``max_chunk_tokens``.
+  ``model.random_init_seed``, ``model.operand_dtype`` ("bf16" default | "fp16": 8x smaller
+  rounding error, ~4 % slower), ``max_chunk_tokens``.
 """
 from __future__ import annotations
 
@@ -178,7 +179,8 @@ def build_scorer(config, device: int = 0) -> PllScorer:
         sd = synth.random_init_state_dict(cfg, int(seed))
     else:
         raise FileNotFoundError(f"checkpoint_path {ckpt!r} not found and model.random_init_seed not set")
-    return PllScorer(sd, cfg, device=device, max_chunk_tokens=int(getattr(config, "max_chunk_tokens", 0) or 0))
+    return PllScorer(sd, cfg, device=device, max_chunk_tokens=int(getattr(config, "max_chunk_tokens", 0) or 0),
+                     operand_dtype=str(getattr(config.model, "operand_dtype", "bf16")))
 
 
 def score_split(config, model: PllScorer, path: str) -> dict:
