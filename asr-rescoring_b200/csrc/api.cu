@@ -63,6 +63,7 @@ struct pllb_context {
   bool fp16 = false;                 // GEMM operand dtype: bf16 (default) or IEEE fp16
   bool has_head = false;             // MLM head weights were supplied (PLL scoring available)
   bool fused_ln = true;              // residual + LayerNorm inside the GEMM epilogue (PLLB_FUSED_LN=0 disables)
+  bool share_l0 = true;              // embeddings + layer-0 QKV on the unique rows of a hypothesis (PLLB_SHARE_L0=0 disables)
   int64_t cap_rows = 0, cap_copies = 0, cap_hyps = 0;
   int vocab_pad = 0, tiles_v = 0;
   std::vector<void*> owned;          // every cudaMalloc of this handle
@@ -196,10 +197,24 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   const pllb_model_desc& d = c->d;
   const int H = d.hidden, I = d.intermediate;
   RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, d.vocab, cls != nullptr, c->plan, s));
-  RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
-                     d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->hidden_bf16, c->fp16, s));
-  RC(launch_rowmajor_to_t32(c->y_f32, c->hidden_f32, n_rows, H, s));
   const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
+  // Layer-0 sharing (encoder_kernels.cu, embed_unique_kernel): the masked copies of a hypothesis
+  // share all rows but one, and everything up to the layer-0 Q/K/V projection is row-wise, so it
+  // runs once per unique row (2L+2 per hypothesis, n_unique in total) instead of once per packed
+  // row (L(L+2)).  Bit-identical; used whenever it at least halves the rows.
+  const int64_t n_unique = 2 * (int64_t)n_copies + 2 * (int64_t)n_hyp;
+  const bool share = c->share_l0 && !cls && 2 * n_unique <= n_rows;
+  if (share) {
+    // unique embeddings: fp32 row-major in y_f32, 16-bit GEMM operand in ctx (free until attention writes it)
+    RC(launch_embed_unique(tokens, tok_off, n_hyp, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b, d.ln_eps,
+                           H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->ctx, c->fp16, s));
+    RC(launch_row_src(c->plan, n_copies, s));
+    RC(launch_rowmajor_to_t32(c->y_f32, c->plan.row_src, c->hidden_f32, n_rows, H, s));
+  } else {
+    RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
+                       d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->hidden_bf16, c->fp16, s));
+    RC(launch_rowmajor_to_t32(c->y_f32, nullptr, c->hidden_f32, n_rows, H, s));
+  }
   // Only the [MASK] row of each copy reaches the MLM head (MLM_PLL/main.py:101), and after the
   // last layer's attention every remaining op is row-wise: the last layer's output
   // projection, LayerNorms and FFN run on the gathered masked rows only (1 row per copy
@@ -207,8 +222,10 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   const bool prune_last = upto_layer < 0 && n_layers > 0;
   for (int l = 0; l < n_layers; ++l) {
     const LayerDev& L = c->layers[l];
-    RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide, n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
-    RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, s));
+    const bool shared_rows = share && l == 0;
+    RC(timed_gemm(c, G_QKV, shared_rows ? c->ctx : c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide,
+                  shared_rows ? n_unique : n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
+    RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, shared_rows, s));
     if (prune_last && l == n_layers - 1) {
       RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
       RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
@@ -453,6 +470,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   c->device = device;
   c->fp16 = d.operand_dtype == 1;
   if (const char* e = getenv("PLLB_FUSED_LN")) c->fused_ln = atoi(e) != 0;
+  if (const char* e = getenv("PLLB_SHARE_L0")) c->share_l0 = atoi(e) != 0;
   cudaStream_t s = 0;
   const int H = d.hidden, I = d.intermediate, V = d.vocab;
   int rc = PLLB_OK;
@@ -529,6 +547,8 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   TRY(dev_alloc(c, &c->plan.mask_row, C));
   TRY(dev_alloc(c, &c->plan.label, C));
   TRY(dev_alloc(c, &c->plan.hyp, C));
+  TRY(dev_alloc(c, &c->plan.uniq_base, C));
+  TRY(dev_alloc(c, &c->plan.row_src, R));
   TRY(dev_alloc(c, &c->hg, C * H));
   TRY(dev_alloc(c, &c->t_f32, C * H));
   TRY(dev_alloc(c, &c->hid_c, align_up(C, 128) * H));

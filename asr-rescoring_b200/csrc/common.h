@@ -83,6 +83,8 @@ struct CopyPlan {          // device arrays, one entry per masked copy of the ch
   int32_t* mask_row;       // packed row index of the [MASK] token
   int32_t* label;          // original token at the masked position
   int32_t* hyp;            // chunk-local hypothesis index
+  int32_t* uniq_base;      // first unique row of the copy's hypothesis (layer-0 sharing)
+  int32_t* row_src;        // [packed rows] unique row every packed row equals (layer-0 sharing)
 };
 
 int launch_expand_plan(const int32_t* tokens, const int32_t* hyp_tok_off, const int32_t* hyp_copy_base,
@@ -101,8 +103,15 @@ int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, con
 // out_bf16 = bf16(LN(x)); no residual (MLM head transform)
 int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const float* b, float eps, int64_t rows,
                          int H, bool fp16, cudaStream_t s);
+// shared_rows: qkv holds the unique rows of every hypothesis (2L+2 per hypothesis) instead of one row per packed row
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
-                     int max_T, bool fp16, cudaStream_t s);
+                     int max_T, bool fp16, bool shared_rows, cudaStream_t s);
+// Embeddings of the unique rows of every hypothesis (fp32 row-major + 16-bit), and the packed-row -> unique-row map.
+int launch_embed_unique(const int32_t* tokens, const int32_t* hyp_tok_off, int32_t n_hyp, const float* word_emb,
+                        const float* pos_emb, const float* type_emb, const float* g, const float* b, float eps, int H,
+                        int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t vocab, float* u_f32, void* u_bf16,
+                        bool fp16, cudaStream_t s);
+int launch_row_src(CopyPlan plan, int32_t n_copies, cudaStream_t s);
 int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
                           int max_T, cudaStream_t s);
 int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out,
@@ -114,7 +123,8 @@ int launch_lse_finish(const float2* partials, const float* label_logit, int32_t 
 int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t n_hyp, double* out_pll,
                    float* out_tok_logp, cudaStream_t s);
 // T32 blocked fp32 [rows, H] -> row-major fp32 (debug / parity output)
-int launch_rowmajor_to_t32(const float* src, float* dst, int64_t rows, int H, cudaStream_t s);
+// row_src (optional): packed row r is read from src row row_src[r]
+int launch_rowmajor_to_t32(const float* src, const int32_t* row_src, float* dst, int64_t rows, int H, cudaStream_t s);
 int launch_t32_to_rowmajor(const float* src, float* dst, int64_t rows, int H, cudaStream_t s);
 int launch_f32_to_bf16(const float* src, void* dst, int64_t n, bool fp16, cudaStream_t s);
 

@@ -63,6 +63,7 @@ __global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int
     plan.mask_row[c0] = r0;
     plan.label[c0] = 0;
     plan.hyp[c0] = h;
+    plan.uniq_base[c0] = 0;
     return;
   }
   for (int m = 0; m < L; ++m) {
@@ -72,6 +73,7 @@ __global__ void expand_plan_kernel(const int32_t* __restrict__ tokens, const int
     plan.mask_row[c] = r0 + m * T + m + 1;
     plan.label[c] = min(max(tokens[t0 + m], 0), vocab - 1);   // ids are validated on the host; clamp = memory safety
     plan.hyp[c] = h;
+    plan.uniq_base[c] = 2 * t0 + 2 * h;                       // sum over earlier hypotheses of (T + L), see embed_unique_kernel
   }
 }
 
@@ -152,6 +154,25 @@ __device__ __forceinline__ void store_row(const float4 (&x)[VEC], float4* __rest
   }
 }
 
+// BertEmbeddings of one token (modeling_bert.py:72-112): (word + token_type(0)) + position -> LayerNorm.
+template <int VEC>
+__device__ __forceinline__ void embed_row(float4 (&x)[VEC], int id, int p, const float* __restrict__ word_emb,
+                                          const float* __restrict__ pos_emb, const float* __restrict__ type_emb,
+                                          const float* __restrict__ g, const float* __restrict__ b, float eps, int lane) {
+  constexpr int H = 128 * VEC;
+  const float4* w = reinterpret_cast<const float4*>(word_emb + (size_t)id * H);
+  const float4* pe = reinterpret_cast<const float4*>(pos_emb + (size_t)p * H);
+  const float4* te = reinterpret_cast<const float4*>(type_emb);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 a = __ldg(w + lane + 32 * i), bb = __ldg(te + lane + 32 * i), cc = __ldg(pe + lane + 32 * i);
+    // (word + token_type) + position — modeling_bert.py:104-108
+    x[i].x = (a.x + bb.x) + cc.x; x[i].y = (a.y + bb.y) + cc.y;
+    x[i].z = (a.z + bb.z) + cc.z; x[i].w = (a.w + bb.w) + cc.w;
+  }
+  ln_normalize<VEC>(x, g, b, eps, lane);
+}
+
 // ---------------------------------------------------------------- stage 1 + BertEmbeddings
 // One warp per masked copy: derives every token id of the copy on the fly (ids never touch
 // HBM), gathers word + position + token_type(0) rows, LayerNorm, writes the fp32 residual
@@ -172,18 +193,8 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
   const int t0 = hyp_tok_off[plan.hyp[c]];
   for (int p = 0; p < T; ++p) {
     const int id = min(max(copy_token_id(tokens, t0, T, m, p, cls_id, sep_id, mask_id), 0), vocab - 1);
-    const float4* w = reinterpret_cast<const float4*>(word_emb + (size_t)id * H);
-    const float4* pe = reinterpret_cast<const float4*>(pos_emb + (size_t)p * H);
-    const float4* te = reinterpret_cast<const float4*>(type_emb);
     float4 x[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float4 a = __ldg(w + lane + 32 * i), bb = __ldg(te + lane + 32 * i), cc = __ldg(pe + lane + 32 * i);
-      // (word + token_type) + position — modeling_bert.py:104-108
-      x[i].x = (a.x + bb.x) + cc.x; x[i].y = (a.y + bb.y) + cc.y;
-      x[i].z = (a.z + bb.z) + cc.z; x[i].w = (a.w + bb.w) + cc.w;
-    }
-    ln_normalize<VEC>(x, g, b, eps, lane);
+    embed_row<VEC>(x, id, p, word_emb, pos_emb, type_emb, g, b, eps, lane);
     const size_t row = (size_t)(start + p);
     // fp32 goes out row-major here (one coalesced 3 KB row per warp); rowmajor_to_t32_kernel
     // re-tiles it into the T32 residual layout with fully coalesced accesses on both sides.
@@ -191,6 +202,55 @@ embed_ln_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ 
     for (int i = 0; i < VEC; ++i) reinterpret_cast<float4*>(hidden_f32 + row * H)[lane + 32 * i] = x[i];
     store_row<VEC, FP16>(x, nullptr, hidden_bf16 + row * H, lane);
   }
+}
+
+// ---------------------------------------------------------------- layer-0 sharing
+// The L masked copies of a hypothesis differ from the unmasked sequence [CLS] t [SEP] in ONE
+// row each, and everything up to and including the layer-0 Q/K/V projection is row-wise.
+// So embeddings and the layer-0 QKV GEMM run on the UNIQUE rows of a hypothesis only:
+//   rows ub .. ub+T-1      the unmasked sequence, position p = row - ub
+//   rows ub+T .. ub+T+L-1  [MASK] at position m+1, m = row - ub - T
+// with ub = sum over earlier hypotheses of (T + L) = 2*tok_off + 2*h.  Row p of copy m maps to
+// unique row (p == m+1 ? ub+T+m : ub+p).  Results are bit-identical to the per-copy path
+// (same per-row arithmetic); 2L+2 rows instead of L(L+2).
+constexpr int UNIQ_PARTS = 4;   // warps per hypothesis
+
+template <int VEC, bool FP16>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+embed_unique_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ hyp_tok_off, int32_t n_hyp,
+                    const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
+                    const float* __restrict__ type_emb, const float* __restrict__ g, const float* __restrict__ b,
+                    float eps, int cls_id, int sep_id, int mask_id, int vocab, float* __restrict__ u_f32,
+                    __nv_bfloat16* __restrict__ u_bf16) {
+  constexpr int H = 128 * VEC;
+  const int w = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int h = w / UNIQ_PARTS, part = w % UNIQ_PARTS;
+  if (h >= n_hyp) return;
+  const int t0 = hyp_tok_off[h];
+  const int L = hyp_tok_off[h + 1] - t0, T = L + 2;
+  const size_t ub = (size_t)2 * t0 + 2 * h;
+  for (int j = part; j < T + L; j += UNIQ_PARTS) {
+    const int p = j < T ? j : j - T + 1;
+    int id = j >= T ? mask_id : (p == 0 ? cls_id : (p == T - 1 ? sep_id : tokens[t0 + p - 1]));
+    id = min(max(id, 0), vocab - 1);
+    float4 x[VEC];
+    embed_row<VEC>(x, id, p, word_emb, pos_emb, type_emb, g, b, eps, lane);
+    const size_t row = ub + j;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) reinterpret_cast<float4*>(u_f32 + row * H)[lane + 32 * i] = x[i];
+    store_row<VEC, FP16>(x, nullptr, u_bf16 + row * H, lane);
+  }
+}
+
+// row_src[packed row] = unique row it equals (one warp per copy)
+__global__ void row_src_kernel(CopyPlan plan, int32_t n_copies) {
+  const int c = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= n_copies) return;
+  const int start = plan.seq_start[c], T = plan.seq_len[c], ub = plan.uniq_base[c];
+  const int mpos = plan.mask_row[c] - start;
+  for (int p = lane; p < T; p += 32) plan.row_src[start + p] = p == mpos ? ub + T + mpos - 1 : ub + p;
 }
 
 // hidden = LayerNorm(y + hidden) in place (+ bf16 copy).  One warp per row.
@@ -345,24 +405,37 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
   }
 }
 
+// Packed row r of a sequence -> element offset of its [Q|K|V] row.  RowDirect: the copy's own rows;
+// RowShared: the unique rows of its hypothesis (layer-0 sharing, see embed_unique_kernel).
+struct RowDirect {
+  size_t start_ld, ld;
+  __device__ __forceinline__ size_t operator()(int r) const { return start_ld + (size_t)r * ld; }
+};
+struct RowShared {
+  int ubase, umask, mpos;
+  size_t ld;
+  __device__ __forceinline__ size_t operator()(int r) const { return (size_t)(r == mpos ? umask : ubase + r) * ld; }
+};
+
 // Streaming form: any T; V blocks staged per 16-key block, Q/K fragments straight from global.
-template <bool FP16>
-__device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb, const __nv_bfloat16* __restrict__ kb,
-                                            const __nv_bfloat16* __restrict__ vb, __nv_bfloat16* __restrict__ ob,
-                                            int T, size_t ld, int H, int lane, __nv_bfloat16* vs) {
+template <bool FP16, class RM>
+__device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ base /* qkv + head*64 */, const RM rm,
+                                            __nv_bfloat16* __restrict__ ob, int T, int H, int lane, __nv_bfloat16* vs) {
+  const __nv_bfloat16* kb = base + H;
+  const __nv_bfloat16* vb = base + 2 * H;
   const int g = lane >> 2, cq = lane & 3;
   const uint32_t vs_addr = (uint32_t)__cvta_generic_to_shared(vs);
   constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // head_dim**-0.5 * log2(e)
 
   for (int m0 = 0; m0 < T; m0 += 16) {
-    const int r0 = min(m0 + g, T - 1), r1 = min(m0 + g + 8, T - 1);
+    const size_t o0 = rm(min(m0 + g, T - 1)), o1 = rm(min(m0 + g + 8, T - 1));
     uint32_t qf[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      qf[ks][0] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ld + 16 * ks + 2 * cq);
-      qf[ks][1] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ld + 16 * ks + 2 * cq);
-      qf[ks][2] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r0 * ld + 16 * ks + 8 + 2 * cq);
-      qf[ks][3] = *reinterpret_cast<const uint32_t*>(qb + (size_t)r1 * ld + 16 * ks + 8 + 2 * cq);
+      qf[ks][0] = *reinterpret_cast<const uint32_t*>(base + o0 + 16 * ks + 2 * cq);
+      qf[ks][1] = *reinterpret_cast<const uint32_t*>(base + o1 + 16 * ks + 2 * cq);
+      qf[ks][2] = *reinterpret_cast<const uint32_t*>(base + o0 + 16 * ks + 8 + 2 * cq);
+      qf[ks][3] = *reinterpret_cast<const uint32_t*>(base + o1 + 16 * ks + 8 + 2 * cq);
     }
     float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
     float o[8][4];
@@ -376,7 +449,7 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
       for (int i = 0; i < 4; ++i) {
         const int row = i * 4 + (lane >> 3), ch = lane & 7;
         const int key = min(k0 + row, T - 1);
-        const uint4 v = *reinterpret_cast<const uint4*>(vb + (size_t)key * ld + ch * 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(vb + rm(key) + ch * 8);
         *reinterpret_cast<uint4*>(vs + row * ATT_VROW + ch * 8) = v;
       }
       // S block = Q K^T for keys k0..k0+15 (two n-tiles of 8 keys)
@@ -385,7 +458,7 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
       for (int j = 0; j < 2; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
         const int key = min(k0 + 8 * j + g, T - 1);
-        const __nv_bfloat16* kr = kb + (size_t)key * ld + 2 * cq;
+        const __nv_bfloat16* kr = kb + rm(key) + 2 * cq;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + 16 * ks);
@@ -467,9 +540,9 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ qb
 constexpr int ATT_TS = 32;
 constexpr int ATT_STAGE_ELEMS = 3 * ATT_TS * ATT_VROW;   // bf16 elements per warp (13.5 KiB)
 
-template <bool FP16>
-__device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb, __nv_bfloat16* __restrict__ ob, int T,
-                                            size_t ld, int H, int lane, __nv_bfloat16* sm) {
+template <bool FP16, class RM>
+__device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ base /* qkv + head*64 */, const RM rm,
+                                            __nv_bfloat16* __restrict__ ob, int T, int H, int lane, __nv_bfloat16* sm) {
   const int g = lane >> 2, cq = lane & 3;
   const uint32_t sm_addr = (uint32_t)__cvta_generic_to_shared(sm);
   constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
@@ -477,13 +550,13 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
   {
     // 3 matrices x T rows x 8 chunks of 16 B; lane -> (row offset, chunk), no integer division
     const int r_off = lane >> 3, ch = lane & 7;
+    for (int r = r_off; r < T; r += 4) {
+      const __nv_bfloat16* src = base + rm(r) + ch * 8;
+      const uint32_t dst = sm_addr + (uint32_t)(r * ATT_VROW + ch * 8) * 2;
 #pragma unroll
-    for (int mat = 0; mat < 3; ++mat) {
-      const __nv_bfloat16* src = qb + (size_t)mat * H + ch * 8;
-      const uint32_t dst = sm_addr + (uint32_t)(mat * ATT_TS * ATT_VROW + ch * 8) * 2;
-      for (int r = r_off; r < T; r += 4)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(r * ATT_VROW) * 2),
-                     "l"(src + (size_t)r * ld) : "memory");
+      for (int mat = 0; mat < 3; ++mat)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(mat * ATT_TS * ATT_VROW) * 2),
+                     "l"(src + (size_t)mat * H) : "memory");
     }
     // V rows T .. ceil16(T)-1 are multiplied by p = 0: they must be finite (0 * NaN = NaN).  K / Q
     // padding rows only produce scores that are replaced by -inf / rows that are never stored.
@@ -602,7 +675,8 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ qb
   }
 }
 
-template <bool FP16>
+// SHARED: qkv holds the unique rows of every hypothesis (layer 0); otherwise one row per packed row.
+template <bool FP16, bool SHARED>
 __global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
                      int32_t n_copies, int H, int NH) {
@@ -614,10 +688,18 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   const int c = (int)(pair / NH), head = (int)(pair % NH);
   const int start = plan.seq_start[c], T = plan.seq_len[c];
   const size_t ld = (size_t)3 * H;
-  const __nv_bfloat16* qb = qkv + (size_t)start * ld + head * 64;
+  const __nv_bfloat16* base = qkv + head * 64;
   __nv_bfloat16* ob = ctx + (size_t)start * H + head * 64;
-  if (T <= ATT_TS) attn_staged<FP16>(qb, ob, T, ld, H, lane, sm);
-  else attn_stream<FP16>(qb, qb + H, qb + 2 * H, ob, T, ld, H, lane, sm);
+  if constexpr (SHARED) {
+    const int ub = plan.uniq_base[c], mpos = plan.mask_row[c] - start;
+    const RowShared rm{ub, ub + T + mpos - 1, mpos, ld};
+    if (T <= ATT_TS) attn_staged<FP16>(base, rm, ob, T, H, lane, sm);
+    else attn_stream<FP16>(base, rm, ob, T, H, lane, sm);
+  } else {
+    const RowDirect rm{(size_t)start * ld, ld};
+    if (T <= ATT_TS) attn_staged<FP16>(base, rm, ob, T, H, lane, sm);
+    else attn_stream<FP16>(base, rm, ob, T, H, lane, sm);
+  }
 }
 
 // ---------------------------------------------------------------- head helpers
@@ -646,7 +728,8 @@ __global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int3
 
 // row-major fp32 [rows, H] -> T32 blocked layout; one CTA per (32-row block, 128-column slab)
 __global__ void __launch_bounds__(256)
-rowmajor_to_t32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int H) {
+rowmajor_to_t32_kernel(const float* __restrict__ src, const int32_t* __restrict__ row_src /* or null */,
+                       float* __restrict__ dst, int64_t rows, int H) {
   __shared__ float tile[32][132];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 128;
@@ -655,7 +738,10 @@ rowmajor_to_t32_kernel(const float* __restrict__ src, float* __restrict__ dst, i
   for (int k = 0; k < 4; ++k) {                               // warp w loads rows w, w+8, w+16, w+24 (512 B each)
     const int r = w + 8 * k;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < rows) v = *reinterpret_cast<const float4*>(src + (r0 + r) * H + c0 + 4 * lane);
+    if (r0 + r < rows) {
+      const int64_t sr = row_src ? (int64_t)row_src[r0 + r] : r0 + r;
+      v = *reinterpret_cast<const float4*>(src + sr * H + c0 + 4 * lane);
+    }
     *reinterpret_cast<float4*>(&tile[r][4 * lane]) = v;
   }
   __syncthreads();
@@ -795,6 +881,28 @@ int launch_embed_ln(const int32_t* tokens, const int32_t* hyp_tok_off, CopyPlan 
   return PLLB_OK;
 }
 
+int launch_embed_unique(const int32_t* tokens, const int32_t* hyp_tok_off, int32_t n_hyp, const float* word_emb,
+                        const float* pos_emb, const float* type_emb, const float* g, const float* b, float eps, int H,
+                        int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t vocab, float* u_f32, void* u_bf16,
+                        bool fp16, cudaStream_t s) {
+  if (n_hyp <= 0) return PLLB_OK;
+  const unsigned grid = (unsigned)ceil_div((int64_t)n_hyp * UNIQ_PARTS, WARPS_PER_BLOCK);
+#define EMU(F) embed_unique_kernel<VEC, F><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(                                      \
+      tokens, hyp_tok_off, n_hyp, word_emb, pos_emb, type_emb, g, b, eps, cls_id, sep_id, mask_id, vocab, u_f32,         \
+      reinterpret_cast<__nv_bfloat16*>(u_bf16))
+  PLLB_DISPATCH_VEC(H, (fp16 ? EMU(true) : EMU(false)));
+#undef EMU
+  PLLB_LAUNCH_CHECK("embed_unique_kernel");
+  return PLLB_OK;
+}
+
+int launch_row_src(CopyPlan plan, int32_t n_copies, cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  row_src_kernel<<<(unsigned)ceil_div(n_copies, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, s>>>(plan, n_copies);
+  PLLB_LAUNCH_CHECK("row_src_kernel");
+  return PLLB_OK;
+}
+
 int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, const float* g, const float* b, float eps,
                        int64_t rows, int H, bool fp16, cudaStream_t s) {
   if (rows <= 0) return PLLB_OK;
@@ -820,23 +928,23 @@ int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const f
 }
 
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH, int max_T,
-                     bool fp16, cudaStream_t s) {
+                     bool fp16, bool shared_rows, cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
   (void)max_T;
   const int64_t pairs = (int64_t)n_copies * NH;
   const int smem = ATT_WARPS * ATT_STAGE_ELEMS * 2;
-  if (fp16) {
-    PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attention_mma_kernel<true><<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
-        NH);
-  } else {
-    PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attention_mma_kernel<false><<<(unsigned)ceil_div(pairs, ATT_WARPS), ATT_WARPS * 32, smem, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
-        NH);
-  }
+  const unsigned grid = (unsigned)ceil_div(pairs, ATT_WARPS);
+#define ATT(F, S)                                                                                                  \
+  do {                                                                                                             \
+    PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    attention_mma_kernel<F, S><<<grid, ATT_WARPS * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), \
+                                                                  reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, \
+                                                                  n_copies, H, NH);                                \
+  } while (0)
+  if (fp16) { if (shared_rows) ATT(true, true); else ATT(true, false); }
+  else { if (shared_rows) ATT(false, true); else ATT(false, false); }
+#undef ATT
   PLLB_LAUNCH_CHECK("attention_mma_kernel");
   return PLLB_OK;
 }
@@ -901,11 +1009,11 @@ int launch_hyp_sum(const float* tok_logp, const int32_t* hyp_copy_base, int32_t 
   return PLLB_OK;
 }
 
-int launch_rowmajor_to_t32(const float* src, float* dst, int64_t rows, int H, cudaStream_t s) {
+int launch_rowmajor_to_t32(const float* src, const int32_t* row_src, float* dst, int64_t rows, int H, cudaStream_t s) {
   if (rows <= 0) return PLLB_OK;
   if (H % 128 != 0) return fail(PLLB_ERR_INVALID, "rowmajor_to_t32: H % 128 != 0");
   dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)(H / 128));
-  rowmajor_to_t32_kernel<<<grid, 256, 0, s>>>(src, dst, rows, H);
+  rowmajor_to_t32_kernel<<<grid, 256, 0, s>>>(src, row_src, dst, rows, H);
   PLLB_LAUNCH_CHECK("rowmajor_to_t32_kernel");
   return PLLB_OK;
 }

@@ -539,3 +539,31 @@ def test_degenerate_batches():
     assert engine.levenshtein([], []).shape == (0,)
     assert engine.levenshtein([""], [""]).tolist() == [0]
     assert engine.levenshtein(["abc"], [""]).tolist() == [3]
+
+
+def test_layer0_sharing_is_bit_identical(monkeypatch):
+    """Embeddings + the layer-0 Q/K/V projection run on the unique rows of a hypothesis (2L+2)
+    instead of on every packed row (L(L+2)); scores, per-token terms and hidden states must be
+    bit-identical to the per-copy path, incl. long sequences (streaming attention), chunks that
+    fall back (only 1-token hypotheses) and chunk boundaries."""
+    cfg = synth.BERT_TINY
+    sd = synth.random_init_state_dict(cfg, 8)
+    rng = np.random.default_rng(12)
+    lens = [1] * 40 + [int(x) for x in rng.integers(1, 40, 150)] + [45, 60, 2, 3, 0, 33, 31, 32]
+    toks = [rng.integers(670, 7000, L).astype(np.int32) for L in lens]
+    off = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    tok = np.concatenate(toks).astype(np.int32)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("PLLB_SHARE_L0", mode)
+        with engine.PllScorer(sd, cfg, max_chunk_tokens=4096) as sc:
+            pll, terms = sc.score_packed(tok, off, return_token_logp=True)
+            flops = sc.stats()["gemm_flops"]
+        with engine.PllScorer(sd, cfg) as sc:
+            h0 = sc.hidden(tok[off[40]:off[60]], off[40:61] - off[40], 0)
+            h1 = sc.hidden(tok[off[40]:off[60]], off[40:61] - off[40], 1)
+        res[mode] = (pll, terms, h0, h1, flops)
+    for a, b in zip(res["1"][:4], res["0"][:4]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert res["1"][4] < res["0"][4]                      # and it executed fewer GEMM FLOPs
