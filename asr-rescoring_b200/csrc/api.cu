@@ -223,11 +223,22 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   for (int l = 0; l < n_layers; ++l) {
     const LayerDev& L = c->layers[l];
     const bool shared_rows = share && l == 0;
-    RC(timed_gemm(c, G_QKV, shared_rows ? c->ctx : c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide,
-                  shared_rows ? n_unique : n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
-    RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, shared_rows, s));
-    if (prune_last && l == n_layers - 1) {
-      RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
+    const bool last = prune_last && l == n_layers - 1;
+    if (last && !shared_rows) {
+      // The pruned last layer consumes one attention row per copy: K|V for every row, Q for that
+      // row only (1/3 of the projection saved), then a single-query attention straight into hg.
+      RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w + (size_t)H * H, L.qkv_b + H, c->wide, n_rows, 2 * H, H,
+                    EPI_BIAS_BF16, nullptr, s));
+      RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->hg, s));
+      RC(timed_gemm(c, G_QKV, c->hg, L.qkv_w, L.qkv_b, c->t_bf16, n_copies, H, H, EPI_BIAS_BF16, nullptr, s));
+      RC(launch_attention_row(c->t_bf16, c->wide, c->hg, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, s));
+    } else {
+      RC(timed_gemm(c, G_QKV, shared_rows ? c->ctx : c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide,
+                    shared_rows ? n_unique : n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
+      RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, shared_rows, s));
+      if (last) RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
+    }
+    if (last) {
       RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
       RC(timed_gemm_ln(c, G_AO, c->hg, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hid_c, c->t_bf16, n_copies, H, s));
       RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s));

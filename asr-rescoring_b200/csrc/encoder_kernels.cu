@@ -702,6 +702,75 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   }
 }
 
+// ---------------------------------------------------------------- last-layer attention
+// Downstream of the last layer only ONE row per copy is consumed (the [MASK] row, or [CLS] for
+// sequence scoring), so its attention has a single query row: q comes from the pruned Q
+// projection [copies, H], K/V of the whole sequence from the K|V projection [rows, 2H].
+// One warp per (copy, head): lane-per-key scores, fp32 softmax, lane-per-dimension-pair P·V.
+constexpr int ATTR_MAXT = 512;
+
+template <bool FP16>
+__device__ __forceinline__ float2 unpack16(uint32_t u) {
+  if constexpr (FP16) return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+attention_row_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
+                     __nv_bfloat16* __restrict__ out, CopyPlan plan, int32_t n_copies, int H, int NH) {
+  __shared__ float qs[WARPS_PER_BLOCK][64];
+  __shared__ float ps[WARPS_PER_BLOCK][ATTR_MAXT];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + w;
+  if (pair >= (int64_t)n_copies * NH) return;
+  const int c = (int)(pair / NH), head = (int)(pair % NH);
+  const int start = plan.seq_start[c], T = plan.seq_len[c];
+  constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // head_dim**-0.5 * log2(e)
+  {
+    const float2 qq = unpack16<FP16>(*reinterpret_cast<const uint32_t*>(q + (size_t)c * H + head * 64 + 2 * lane));
+    qs[w][2 * lane] = qq.x * kScaleLog2;
+    qs[w][2 * lane + 1] = qq.y * kScaleLog2;
+  }
+  __syncwarp();
+  const size_t ld = (size_t)2 * H;
+  const __nv_bfloat16* kb = kv + (size_t)start * ld + head * 64;
+  const __nv_bfloat16* vb = kb + H;
+  float mx = -INFINITY;
+  for (int j = lane; j < T; j += 32) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * ld);
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = kr[i];
+      const float2 a = unpack16<FP16>(u.x), b = unpack16<FP16>(u.y), cc = unpack16<FP16>(u.z), d = unpack16<FP16>(u.w);
+      const float* qv = &qs[w][8 * i];
+      sc += (a.x * qv[0] + a.y * qv[1]) + (b.x * qv[2] + b.y * qv[3]) + (cc.x * qv[4] + cc.y * qv[5]) +
+            (d.x * qv[6] + d.y * qv[7]);
+    }
+    ps[w][j] = sc;
+    mx = fmaxf(mx, sc);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float pj = exp2f(ps[w][j] - mx);
+    ps[w][j] = pj;
+    sum += pj;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = 0; j < T; ++j) {
+    const float pj = ps[w][j];
+    const float2 v = unpack16<FP16>(*reinterpret_cast<const uint32_t*>(vb + (size_t)j * ld + 2 * lane));
+    a0 += pj * v.x;
+    a1 += pj * v.y;
+  }
+  const float inv = 1.0f / sum;
+  *reinterpret_cast<uint32_t*>(out + (size_t)c * H + head * 64 + 2 * lane) = pack16<FP16>(a0 * inv, a1 * inv);
+}
+
 // ---------------------------------------------------------------- head helpers
 __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows,
                                         int32_t n, int H, __nv_bfloat16* __restrict__ dst) {
@@ -946,6 +1015,24 @@ int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_
   else { if (shared_rows) ATT(false, true); else ATT(false, false); }
 #undef ATT
   PLLB_LAUNCH_CHECK("attention_mma_kernel");
+  return PLLB_OK;
+}
+
+int launch_attention_row(const void* q_bf16, const void* kv_bf16, void* out_bf16, CopyPlan plan, int32_t n_copies, int H,
+                         int NH, int max_T, bool fp16, cudaStream_t s) {
+  if (n_copies <= 0) return PLLB_OK;
+  if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
+  if (max_T > ATTR_MAXT) return fail(PLLB_ERR_TOO_LONG, "attention_row: sequence longer than 512 rows");
+  const unsigned grid = (unsigned)ceil_div((int64_t)n_copies * NH, WARPS_PER_BLOCK);
+  if (fp16)
+    attention_row_kernel<true><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q_bf16), reinterpret_cast<const __nv_bfloat16*>(kv_bf16),
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), plan, n_copies, H, NH);
+  else
+    attention_row_kernel<false><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(q_bf16), reinterpret_cast<const __nv_bfloat16*>(kv_bf16),
+        reinterpret_cast<__nv_bfloat16*>(out_bf16), plan, n_copies, H, NH);
+  PLLB_LAUNCH_CHECK("attention_row_kernel");
   return PLLB_OK;
 }
 
