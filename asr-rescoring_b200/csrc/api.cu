@@ -63,6 +63,7 @@ struct pllb_context {
   bool fp16 = false;                 // GEMM operand dtype: bf16 (default) or IEEE fp16
   bool has_head = false;             // MLM head weights were supplied (PLL scoring available)
   bool fused_ln = true;              // residual + LayerNorm inside the GEMM epilogue (PLLB_FUSED_LN=0 disables)
+  bool prune_q = true;               // last layer: Q projection + attention for the consumed row only (PLLB_PRUNE_Q=0 disables)
   bool share_l0 = true;              // embeddings + layer-0 QKV on the unique rows of a hypothesis (PLLB_SHARE_L0=0 disables)
   int64_t cap_rows = 0, cap_copies = 0, cap_hyps = 0;
   int vocab_pad = 0, tiles_v = 0;
@@ -224,7 +225,7 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
     const LayerDev& L = c->layers[l];
     const bool shared_rows = share && l == 0;
     const bool last = prune_last && l == n_layers - 1;
-    if (last && !shared_rows) {
+    if (last && !shared_rows && c->prune_q) {
       // The pruned last layer consumes one attention row per copy: K|V for every row, Q for that
       // row only (1/3 of the projection saved), then a single-query attention straight into hg.
       RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w + (size_t)H * H, L.qkv_b + H, c->wide, n_rows, 2 * H, H,
@@ -482,6 +483,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   c->fp16 = d.operand_dtype == 1;
   if (const char* e = getenv("PLLB_FUSED_LN")) c->fused_ln = atoi(e) != 0;
   if (const char* e = getenv("PLLB_SHARE_L0")) c->share_l0 = atoi(e) != 0;
+  if (const char* e = getenv("PLLB_PRUNE_Q")) c->prune_q = atoi(e) != 0;
   cudaStream_t s = 0;
   const int H = d.hidden, I = d.intermediate, V = d.vocab;
   int rc = PLLB_OK;
