@@ -719,7 +719,6 @@ template <bool FP16>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 attention_row_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
                      __nv_bfloat16* __restrict__ out, CopyPlan plan, int32_t n_copies, int H, int NH) {
-  __shared__ float qs[WARPS_PER_BLOCK][64];
   __shared__ float ps[WARPS_PER_BLOCK][ATTR_MAXT];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t pair = (int64_t)blockIdx.x * WARPS_PER_BLOCK + w;
@@ -727,48 +726,65 @@ attention_row_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   const int c = (int)(pair / NH), head = (int)(pair % NH);
   const int start = plan.seq_start[c], T = plan.seq_len[c];
   constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;   // head_dim**-0.5 * log2(e)
+  // lane = (key slot r_off, 16-byte chunk ch): a warp access covers 4 rows x 128 contiguous bytes
+  const int r_off = lane >> 3, ch = lane & 7;
+  float qv[8];
   {
-    const float2 qq = unpack16<FP16>(*reinterpret_cast<const uint32_t*>(q + (size_t)c * H + head * 64 + 2 * lane));
-    qs[w][2 * lane] = qq.x * kScaleLog2;
-    qs[w][2 * lane + 1] = qq.y * kScaleLog2;
+    const uint4 u = *reinterpret_cast<const uint4*>(q + (size_t)c * H + head * 64 + ch * 8);
+    const float2 a = unpack16<FP16>(u.x), b = unpack16<FP16>(u.y), cc = unpack16<FP16>(u.z), d = unpack16<FP16>(u.w);
+    qv[0] = a.x * kScaleLog2; qv[1] = a.y * kScaleLog2; qv[2] = b.x * kScaleLog2; qv[3] = b.y * kScaleLog2;
+    qv[4] = cc.x * kScaleLog2; qv[5] = cc.y * kScaleLog2; qv[6] = d.x * kScaleLog2; qv[7] = d.y * kScaleLog2;
   }
-  __syncwarp();
   const size_t ld = (size_t)2 * H;
-  const __nv_bfloat16* kb = kv + (size_t)start * ld + head * 64;
+  const __nv_bfloat16* kb = kv + (size_t)start * ld + head * 64 + ch * 8;
   const __nv_bfloat16* vb = kb + H;
   float mx = -INFINITY;
-  for (int j = lane; j < T; j += 32) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)j * ld);
+  for (int j0 = 0; j0 < T; j0 += 4) {                       // warp-uniform trip count
+    const int j = j0 + r_off;
     float sc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 u = kr[i];
+    if (j < T) {
+      const uint4 u = *reinterpret_cast<const uint4*>(kb + (size_t)j * ld);
       const float2 a = unpack16<FP16>(u.x), b = unpack16<FP16>(u.y), cc = unpack16<FP16>(u.z), d = unpack16<FP16>(u.w);
-      const float* qv = &qs[w][8 * i];
-      sc += (a.x * qv[0] + a.y * qv[1]) + (b.x * qv[2] + b.y * qv[3]) + (cc.x * qv[4] + cc.y * qv[5]) +
-            (d.x * qv[6] + d.y * qv[7]);
+      sc = (a.x * qv[0] + a.y * qv[1]) + (b.x * qv[2] + b.y * qv[3]) + (cc.x * qv[4] + cc.y * qv[5]) +
+           (d.x * qv[6] + d.y * qv[7]);
     }
-    ps[w][j] = sc;
-    mx = fmaxf(mx, sc);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    if (j < T) {
+      if (ch == 0) ps[w][j] = sc;
+      mx = fmaxf(mx, sc);
+    }
   }
   mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < T; j += 32) {
-    const float pj = exp2f(ps[w][j] - mx);
-    ps[w][j] = pj;
-    sum += pj;
-  }
-  sum = warp_sum(sum);
   __syncwarp();
-  float a0 = 0.f, a1 = 0.f;
-  for (int j = 0; j < T; ++j) {
-    const float pj = ps[w][j];
-    const float2 v = unpack16<FP16>(*reinterpret_cast<const uint32_t*>(vb + (size_t)j * ld + 2 * lane));
-    a0 += pj * v.x;
-    a1 += pj * v.y;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sum = 0.f;
+  for (int j = r_off; j < T; j += 4) {
+    const float pj = exp2f(ps[w][j] - mx);
+    sum += pj;
+    const uint4 u = *reinterpret_cast<const uint4*>(vb + (size_t)j * ld);
+    const float2 a = unpack16<FP16>(u.x), b = unpack16<FP16>(u.y), cc = unpack16<FP16>(u.z), d = unpack16<FP16>(u.w);
+    acc[0] += pj * a.x; acc[1] += pj * a.y; acc[2] += pj * b.x; acc[3] += pj * b.y;
+    acc[4] += pj * cc.x; acc[5] += pj * cc.y; acc[6] += pj * d.x; acc[7] += pj * d.y;
   }
-  const float inv = 1.0f / sum;
-  *reinterpret_cast<uint32_t*>(out + (size_t)c * H + head * 64 + 2 * lane) = pack16<FP16>(a0 * inv, a1 * inv);
+  // combine the four key slots (lanes with equal ch)
+  sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  if (r_off == 0) {
+    const float inv = 1.0f / sum;
+    uint4 o;
+    o.x = pack16<FP16>(acc[0] * inv, acc[1] * inv);
+    o.y = pack16<FP16>(acc[2] * inv, acc[3] * inv);
+    o.z = pack16<FP16>(acc[4] * inv, acc[5] * inv);
+    o.w = pack16<FP16>(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(out + (size_t)c * H + head * 64 + ch * 8) = o;
+  }
 }
 
 // ---------------------------------------------------------------- head helpers
