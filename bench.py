@@ -214,6 +214,11 @@ def main():
     _claim_stdout()
     if args.operand_dtype is None:
         args.operand_dtype = "fp16" if args.workload == "c4" else "bf16"
+    if args.workload == "c4" and not args.utts:
+        # the full C4 list (358 800 hypotheses of 8..64 tokens on a 24-layer encoder) is ~6 minutes
+        # PER PASS on one B200; the bench line for it is quoted on a 150-utterance sample
+        args.utts = 150
+        print("bench: workload c4 runs on the first 150 utterances unless --utts is given", file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
 
