@@ -189,3 +189,31 @@ def test_char_table_agrees_with_the_wordpiece_tokenizer(tmp_path):
     st = syn.char_table()
     for text in ("你好嗎", "abc 1", "龘\u3000x"):
         assert _table_lookup_reference(st, text) == syn.encode(text)
+
+
+def test_encode_batch_merges_device_and_host_paths(tmp_path, monkeypatch):
+    """Host logic of tokenizer.encode_batch with the device call replaced by its numpy restatement:
+    flagged hypotheses are re-tokenised on the host and spliced back in order."""
+    from asr_rescoring_b200 import engine, tokenizer as tkmod
+
+    def fake_tokenize_packed(table, cp, cp_off):
+        ids, off, flag = [], [0], []
+        for i in range(len(cp_off) - 1):
+            text = "".join(chr(c) for c in cp[cp_off[i]:cp_off[i + 1]])
+            r = _table_lookup_reference(table, text)
+            flag.append(1 if r is None else 0)
+            ids += r or []
+            off.append(len(ids))
+        return np.array(ids, np.int32), np.array(off, np.int64), np.array(flag, np.uint8)
+
+    monkeypatch.setattr(engine, "tokenize_packed", fake_tokenize_packed)
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", "你", "好", "嗎", "a", "ab", "##c", "1", "##2", ",", "。", "hello"]
+    vp = tmp_path / "vocab.txt"
+    vp.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    tk = BertCharTokenizer(str(vp))
+    strings = ["你好", "abc", "", "你 好，嗎", "hello 12", "好", "a你", "。。", "12"]
+    for sel in (strings, strings[::-1], ["abc", "12"], ["你好", "嗎"], []):
+        ids, off = tkmod.encode_batch(tk, sel)
+        assert off.tolist() == np.concatenate([[0], np.cumsum([len(tk.encode(x)) for x in sel])]).astype(int).tolist()
+        for i, x in enumerate(sel):
+            assert ids[off[i]:off[i + 1]].tolist() == tk.encode(x), x
