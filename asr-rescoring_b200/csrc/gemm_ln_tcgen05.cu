@@ -22,6 +22,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -66,6 +68,7 @@ struct LnParams {
   const float* gamma;
   const float* beta;
   float eps;
+  int amc;                // 1: the A tile is TMA-multicast to the CN CTAs of the cluster (each issues a share of its 32-row boxes)
 };
 
 template <bool FP16>
@@ -206,6 +209,13 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_m = (p.M + BM - 1) / BM;
   const int num_kb = p.K / BK;
   const int n0 = (int)rank * BN;
+  // All CN CTAs of a cluster multiply the SAME 128 x K block of A by their own 256 columns of W.
+  // With amc the A stage (four 32-row boxes) is fetched from L2 once per cluster: CTA r issues
+  // boxes r, r+CN, ... as TMA multicasts into every CTA's stage, and a stage is reused only after
+  // every CTA's MMAs released it (their commits are multicast to all empty barriers).
+  const bool amc = CN > 1 && p.amc != 0;
+  constexpr uint16_t mask_all = (uint16_t)((1u << CN) - 1u);
+  constexpr int A_BOX_ROWS = 32, A_BOX_BYTES = A_BOX_ROWS * BK * 2;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -215,7 +225,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(bar_full + 8 * s, 1);
-        mbar_init(bar_empty + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, amc ? CN : 1);          // multicast A: every CTA of the cluster releases the stage
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
@@ -242,8 +252,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, bar_full + 8 * stage, kb * BK, m0);
           tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
+          if (amc) {
+            for (int b = (int)rank; b < BM / A_BOX_ROWS; b += CN)
+              tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, kb * BK,
+                                    m0 + b * A_BOX_ROWS, mask_all);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BM / A_BOX_ROWS; ++b)
+              tma_load_2d(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, kb * BK,
+                          m0 + b * A_BOX_ROWS);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -266,7 +285,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tcgen05_mma_bf16(d_tmem, make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2),
                              make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(bar_empty + 8 * stage);
+          if (amc) tcgen05_commit_multicast(bar_empty + 8 * stage, mask_all);
+          else tcgen05_commit(bar_empty + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(bar_tfull + 8 * acc);
@@ -530,10 +550,11 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
   CUtensorMap ta, tb, t16;
   int rc;
-  if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, BM, BK))) return rc;
+  if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
   if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, BN, BK))) return rc;
   if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
-  LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps};
+  static const int amc = [] { const char* e = getenv("PLLB_LN_AMC"); return e ? atoi(e) : 1; }();
+  LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps, amc};
   const int64_t tiles_m = ceil_div(M, BM);
   // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
   const bool staged = K <= H;
