@@ -115,8 +115,6 @@ int launch_row_src(CopyPlan plan, int32_t n_copies, cudaStream_t s);
 // last layer: one query row per copy (q [copies,H]) against the K|V projection of the whole sequence (kv [rows,2H])
 int launch_attention_row(const void* q_bf16, const void* kv_bf16, void* out_bf16, CopyPlan plan, int32_t n_copies, int H,
                          int NH, int max_T, bool fp16, cudaStream_t s);
-int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
-                          int max_T, cudaStream_t s);
 int launch_gather_rows_bf16(const void* hidden_bf16, const int32_t* rows, int32_t n, int H, void* out,
                             cudaStream_t s);
 int launch_gather_rows_f32(const float* src, const int32_t* rows, int32_t n, int H, float* out, cudaStream_t s);

@@ -278,107 +278,6 @@ ln_kernel(const float* __restrict__ y, float* __restrict__ hidden_f32, __nv_bflo
   store_row<VEC, FP16>(x, RESID ? t32_row<VEC>(hidden_f32, row) : nullptr, out_bf16 + row * H, lane);
 }
 
-// ---------------------------------------------------------------- varlen self-attention
-// One warp per (masked copy, head).  K^T and V of the head are staged in shared memory as
-// bf16; 4 query rows are processed together; softmax in fp32 with an online update over
-// 32-key tiles, so any T up to max_position works.  qkv row layout: [Q(H) | K(H) | V(H)].
-constexpr int ATT_QB = 4;
-
-__global__ void attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
-                                 int32_t n_copies, int H, int NH, int Tp /* padded T, odd */, int warps_per_block) {
-  extern __shared__ uint8_t att_smem[];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t pair = (int64_t)blockIdx.x * warps_per_block + wib;
-  if (pair >= (int64_t)n_copies * NH) return;
-  const int c = (int)(pair / NH), head = (int)(pair % NH);
-  const int start = plan.seq_start[c], T = plan.seq_len[c];
-  // per-warp shared memory: Kt[64][Tp] bf16 | V[Tp][64] bf16 | qs[64][4] f32 | ps[32][4] f32
-  const size_t per_warp = (size_t)64 * Tp * 2 + (size_t)Tp * 64 * 2 + 64 * ATT_QB * 4 + 32 * ATT_QB * 4;
-  uint8_t* base = att_smem + (size_t)wib * ((per_warp + 15) & ~(size_t)15);
-  __nv_bfloat16* Kt = reinterpret_cast<__nv_bfloat16*>(base);
-  __nv_bfloat16* Vs = Kt + 64 * Tp;
-  float* qs = reinterpret_cast<float*>(Vs + (size_t)Tp * 64);
-  float* ps = qs + 64 * ATT_QB;
-  const size_t ld = (size_t)3 * H;
-  const __nv_bfloat16* qbase = qkv + (size_t)start * ld + head * 64;
-  const __nv_bfloat16* kbase = qbase + H;
-  const __nv_bfloat16* vbase = qbase + 2 * H;
-
-  for (int j = 0; j < T; ++j) {
-    const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(kbase + (size_t)j * ld + 2 * lane);
-    const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(vbase + (size_t)j * ld + 2 * lane);
-    Kt[(2 * lane) * Tp + j] = k2.x;
-    Kt[(2 * lane + 1) * Tp + j] = k2.y;
-    *reinterpret_cast<__nv_bfloat162*>(Vs + (size_t)j * 64 + 2 * lane) = v2;
-  }
-  __syncwarp();
-
-  for (int i0 = 0; i0 < T; i0 += ATT_QB) {
-    // stage the query block: qs[d][a] = Q[i0+a][d]
-#pragma unroll
-    for (int a = 0; a < ATT_QB; ++a) {
-      const int i = min(i0 + a, T - 1);
-      const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(qbase + (size_t)i * ld + 2 * lane);
-      qs[(2 * lane) * ATT_QB + a] = __bfloat162float(q2.x);
-      qs[(2 * lane + 1) * ATT_QB + a] = __bfloat162float(q2.y);
-    }
-    __syncwarp();
-    float mx[ATT_QB], l[ATT_QB], o0[ATT_QB], o1[ATT_QB];
-#pragma unroll
-    for (int a = 0; a < ATT_QB; ++a) { mx[a] = -INFINITY; l[a] = 0.f; o0[a] = 0.f; o1[a] = 0.f; }
-    for (int kt = 0; kt < T; kt += 32) {
-      const int key = kt + lane;
-      const bool valid = key < T;
-      const int keyc = valid ? key : T - 1;
-      float s[ATT_QB];
-#pragma unroll
-      for (int a = 0; a < ATT_QB; ++a) s[a] = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < 64; ++d) {
-        const float kv = __bfloat162float(Kt[d * Tp + keyc]);
-        const float4 q4 = *reinterpret_cast<const float4*>(qs + d * ATT_QB);
-        s[0] += q4.x * kv; s[1] += q4.y * kv; s[2] += q4.z * kv; s[3] += q4.w * kv;
-      }
-      float p[ATT_QB];
-#pragma unroll
-      for (int a = 0; a < ATT_QB; ++a) {
-        const float sc = valid ? s[a] * 0.125f : -INFINITY;    // scaling = head_dim ** -0.5
-        const float tmax = warp_max(sc);
-        const float nm = fmaxf(mx[a], tmax);
-        p[a] = valid ? __expf(sc - nm) : 0.f;
-        const float tsum = warp_sum(p[a]);
-        const float corr = __expf(mx[a] - nm);                 // exp(-inf) = 0 on the first tile
-        l[a] = l[a] * corr + tsum;
-        o0[a] *= corr; o1[a] *= corr;
-        mx[a] = nm;
-      }
-      __syncwarp();
-      *reinterpret_cast<float4*>(ps + lane * ATT_QB) = make_float4(p[0], p[1], p[2], p[3]);
-      __syncwarp();
-      const int nk = min(32, T - kt);
-      for (int j = 0; j < nk; ++j) {
-        const float4 p4 = *reinterpret_cast<const float4*>(ps + j * ATT_QB);
-        const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(Vs + (size_t)(kt + j) * 64 + 2 * lane);
-        const float vx = __bfloat162float(v2.x), vy = __bfloat162float(v2.y);
-        o0[0] += p4.x * vx; o1[0] += p4.x * vy;
-        o0[1] += p4.y * vx; o1[1] += p4.y * vy;
-        o0[2] += p4.z * vx; o1[2] += p4.z * vy;
-        o0[3] += p4.w * vx; o1[3] += p4.w * vy;
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < ATT_QB; ++a) {
-      const int i = i0 + a;
-      if (i < T) {
-        const float inv = 1.0f / l[a];
-        *reinterpret_cast<__nv_bfloat162*>(ctx + (size_t)(start + i) * H + head * 64 + 2 * lane) =
-            __floats2bfloat162_rn(o0[a] * inv, o1[a] * inv);
-      }
-    }
-    __syncwarp();
-  }
-}
-
 // ---------------------------------------------------------------- tensor-core varlen attention
 // One warp per (masked copy, head), flash-style: 16-query tiles x 16-key blocks with an
 // online softmax, S = Q K^T and O = P V on mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
@@ -1049,27 +948,6 @@ int launch_attention_row(const void* q_bf16, const void* kv_bf16, void* out_bf16
         reinterpret_cast<const __nv_bfloat16*>(q_bf16), reinterpret_cast<const __nv_bfloat16*>(kv_bf16),
         reinterpret_cast<__nv_bfloat16*>(out_bf16), plan, n_copies, H, NH);
   PLLB_LAUNCH_CHECK("attention_row_kernel");
-  return PLLB_OK;
-}
-
-// fp32 SIMT attention (validation kernel: tests compare the tensor-core kernel against it)
-int launch_attention_simt(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
-                          int max_T, cudaStream_t s) {
-  if (n_copies <= 0) return PLLB_OK;
-  if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
-  const int Tp = max_T | 1;
-  size_t per_warp = (size_t)64 * Tp * 2 + (size_t)Tp * 64 * 2 + 64 * ATT_QB * 4 + 32 * ATT_QB * 4;
-  per_warp = (per_warp + 15) & ~(size_t)15;
-  int wpb = 8;
-  while (wpb > 1 && per_warp * wpb > 96 * 1024) wpb >>= 1;
-  const size_t smem = per_warp * wpb;
-  if (smem > 200 * 1024) return fail(PLLB_ERR_TOO_LONG, "attention: sequence too long for shared memory");
-  PLLB_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t pairs = (int64_t)n_copies * NH;
-  attention_kernel<<<(unsigned)ceil_div(pairs, wpb), wpb * 32, smem, s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H,
-      NH, Tp, wpb);
-  PLLB_LAUNCH_CHECK("attention_kernel");
   return PLLB_OK;
 }
 
