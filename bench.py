@@ -13,8 +13,11 @@ random-init bert-base-chinese (BASELINE.json configs[1]); synthetic data (synth.
 value  : device-resident inputs, whole job, max over ranks, CUDA-event timed.
 e2e    : the same through the host-buffer C-ABI calls (pllb_score_host,
          pllb_levenshtein_host, pllb_rescore_sweep_host): H2D and D2H inside the timing.
-roofline: the GEMM kernel (all launches of the timed steps), algorithmic GEMM FLOPs /
-         summed launch durations from CUDA events recorded on the launch stream.
+roofline: the GEMM kernels (all launches of the last timed step), EXECUTED GEMM FLOPs (sum of
+         2*M*N*K over the launches: the layer-0 projection runs on unique rows and the last
+         layer on the consumed rows only, so this is below the SURVEY formula, which is also
+         reported) / summed launch durations from CUDA events recorded on the launch stream.
+stdout : exactly one JSON line (library banners are redirected to stderr).
 cpu_baseline / --impl reference: the oracle port of the reference's torch CPU path
          (oracle/pll_oracle.py) on a bounded sample, all host threads.
 """
