@@ -217,3 +217,22 @@ def test_encode_batch_merges_device_and_host_paths(tmp_path, monkeypatch):
         assert off.tolist() == np.concatenate([[0], np.cumsum([len(tk.encode(x)) for x in sel])]).astype(int).tolist()
         for i, x in enumerate(sel):
             assert ids[off[i]:off[i + 1]].tolist() == tk.encode(x), x
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference runs on the host cores alone (no GPU): exactly one line on
+    stdout, carrying the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1", "--cpu-sample-hyps", "10"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "N-best PLL hypotheses/sec" and d["unit"] == "hyps/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
