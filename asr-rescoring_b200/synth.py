@@ -5,10 +5,13 @@ The reference ships no hypothesis text and no checkpoints (SURVEY.md §2 row 12,
 parity tests use data synthesised from statistics of the reference's fixtures
 (recorded below as plain numbers) following SURVEY.md §8(d):
 
-  * utterance lengths: histogram of espnet_data/alfred/test/ref_text.json
-    (7 176 refs, 104 765 chars, min 3 / mean 14.6 / max 37);
-  * per-hypothesis edit counts: histogram of round(hyps_cer * len(ref)) over
-    espnet_data/alfred/test/hyps_cer.json (71 760 entries);
+  * utterance lengths: the length list of espnet_data/alfred/test/ref_text.json in
+    utterance order (7 176 refs, 104 765 chars, min 3 / mean 14.6 / max 37) —
+    data/aishell1_test_shape.json, written by tools/make_synth_shape.py;
+  * per-hypothesis edit counts: round(hyps_cer * len(ref)) of
+    espnet_data/alfred/test/hyps_cer.json per (utterance, k) from the same table
+    (71 760 entries); hypotheses 11..50 and the length-stretched config 4 draw
+    from its histogram;
   * AM scores: first-best mean/std and mean successive gaps of
     espnet_data/alfred/test/hyps_score.json;
   * token ids: no vocab.txt offline -> id = 670 + rank(char) mod 7322, inside
@@ -91,8 +94,22 @@ class SynthNbest:
         return tok, off
 
 
-def _length_pool() -> np.ndarray:
-    return np.repeat(np.array(list(REF_LEN_HIST.keys())), np.array(list(REF_LEN_HIST.values())))
+_SHAPE = None
+
+
+def shape_table():
+    """(ref_len int64[7176], edits int64[7176, 10]) of the AISHELL-1 test set, utterance order."""
+    global _SHAPE
+    if _SHAPE is None:
+        import json
+        import os
+        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "aishell1_test_shape.json")
+        d = json.load(open(p))
+        ref_len = np.array(d["ref_len"], np.int64)
+        edits = np.array([[int(c, 36) for c in row] for row in d["edits_base36_per_utt"]], np.int64)
+        assert ref_len.shape == (7176,) and edits.shape == (7176, 10)
+        _SHAPE = (ref_len, edits)
+    return _SHAPE
 
 
 def make_nbest(n_utts: int = 7176, n_best: int = 10, seed: int = 0,
@@ -101,15 +118,13 @@ def make_nbest(n_utts: int = 7176, n_best: int = 10, seed: int = 0,
     lengths are drawn uniformly from [min_len, max_len] instead (config 4:
     8..64)."""
     rng = np.random.default_rng(seed)
-    pool = _length_pool()
-    rng.shuffle(pool)
-    if min_len is not None or max_len is not None:
+    ref_len, ref_edits = shape_table()
+    stretched = min_len is not None or max_len is not None
+    if stretched:
         lo, hi = min_len or 3, max_len or 37
         lens = rng.integers(lo, hi + 1, size=n_utts)
-    elif n_utts <= len(pool):
-        lens = pool[:n_utts]
     else:
-        lens = np.concatenate([pool, rng.choice(pool, n_utts - len(pool))])
+        lens = ref_len[np.arange(n_utts) % len(ref_len)]       # utterance order; config 1 = the first 100
     # Zipf-ish unigram distribution over N_DISTINCT_CHARS characters
     p = 1.0 / (np.arange(N_DISTINCT_CHARS) + 10.0)
     p /= p.sum()
@@ -128,7 +143,10 @@ def make_nbest(n_utts: int = 7176, n_best: int = 10, seed: int = 0,
         d = rng.choice(ed_vals, size=n_best, p=ed_p)
         if n_best > 10:
             d[10:] += 1
-        d = d[np.argsort(d + rng.uniform(0, 1.5, size=n_best), kind="stable")]
+        if stretched:
+            d = d[np.argsort(d + rng.uniform(0, 1.5, size=n_best), kind="stable")]
+        else:                                   # the real per-(utterance, k) edit counts for k < 10
+            d[:min(n_best, 10)] = ref_edits[u % len(ref_len), :min(n_best, 10)]
         hs = []
         for k in range(n_best):
             h = list(ref)

@@ -24,8 +24,12 @@ def test_synth_is_deterministic_and_aishell_shaped():
     assert all(len(h) >= 1 for hs in a.hyps for h in hs)
     tok, off = a.packed_tokens()
     assert tok.min() >= 670 and tok.max() < 670 + 7322 and len(off) == 501
-    full = synth._length_pool()
-    assert len(full) == 7176 and int(full.sum()) == 104765  # espnet_data/alfred/test/ref_text.json
+    ref_len, edits = synth.shape_table()                   # espnet_data/alfred/test/{ref_text,hyps_cer}.json
+    assert len(ref_len) == 7176 and int(ref_len.sum()) == 104765 and int(edits.sum()) == 118889
+    hist = dict(zip(*np.unique(ref_len, return_counts=True)))
+    assert hist == synth.REF_LEN_HIST
+    assert dict(zip(*np.unique(edits, return_counts=True))) == synth.EDIT_HIST
+    assert [len(r) for r in a.refs] == list(ref_len[:50]) and np.array_equal(a.edits, edits[:50])
 
 
 def test_random_init_keys_match_hf_state_dict_names():
