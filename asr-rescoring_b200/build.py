@@ -38,16 +38,32 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link; safe when every rank of a torchrun job calls it at once: an exclusive
+    file lock serialises the builders, the late ones find a fresh library and return, and the
+    library appears atomically (linked to a temporary name, then os.replace)."""
     if not force and not _stale():
         return LIB
-    nvcc = _nvcc()
+    import fcntl
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while we waited
+                return LIB
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir: str, verbose: bool) -> str:
+    nvcc = _nvcc()
     objs = []
     procs = []
+    defs = [f"-D{d}" for d in os.environ.get("PLLB_DEFINES", "").split()]     # e.g. PLLB_SPIN_LIMIT=0
     for src, extra in UNITS.items():
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *COMMON, *defs, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
@@ -57,12 +73,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write(log[-1])
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [nvcc, *ARCH, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fPIC", "-ldl"]
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append(f"$ {' '.join(cmd)}\n{out.stdout}")
     if out.returncode != 0:
         sys.stderr.write(log[-1])
         raise RuntimeError("link failed")
+    os.replace(tmp, LIB)
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -2,9 +2,12 @@
 // chunked PLL scoring pipeline, host-buffer wrappers and parity/debug hooks.
 #include <cuda_bf16.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "common.h"
@@ -31,6 +34,68 @@ int sm_count() {
   return cached;
 }
 
+// ---- cached tensor maps --------------------------------------------------------------
+// A CUtensorMap depends only on (base, dtype, element size, rows, cols, box): a scoring pass
+// re-launches the same handful of shapes on the same workspace buffers for every layer of every
+// chunk, so the ~900 cuTensorMapEncodeTiled calls of a C2 step collapse into a few dozen.
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols;
+  uint32_t box_rows, box_cols, dt_elt;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && box_cols == o.box_cols &&
+           dt_elt == o.dt_elt;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (((uint64_t)k.box_rows << 40) | ((uint64_t)k.box_cols << 16) | k.dt_elt) + (h << 6) + (h >> 2);
+    return (size_t)h;
+  }
+};
+thread_local std::unordered_map<TmapKey, CUtensorMap, TmapHash> g_tmaps;
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return (EncodeTiledFn) nullptr;
+  }();
+  return fn;
+}
+}  // namespace
+
+int get_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows, uint64_t cols,
+                uint32_t box_rows, uint32_t box_cols) {
+  const TmapKey key{base, rows, cols, box_rows, box_cols, ((uint32_t)dt << 8) | (uint32_t)elt_bytes};
+  auto it = g_tmaps.find(key);
+  if (it != g_tmaps.end()) {
+    *out = it->second;
+    return PLLB_OK;
+  }
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * (uint64_t)elt_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
+  if (g_tmaps.size() >= 4096) g_tmaps.clear();
+  g_tmaps.emplace(key, *out);
+  return PLLB_OK;
+}
+
 }  // namespace pllb
 
 using namespace pllb;
@@ -48,6 +113,13 @@ struct ClsHead {        // Linear(H, 1) applied to the [CLS] state (device point
   const float* w;
   float b;
   float* out;
+};
+
+// NVTX range (visible in nsys / ncu --nvtx; a no-op without a tool attached)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  void next(const char* name) { nvtxRangePop(); nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
 };
 
 struct TimedLaunch {
@@ -87,6 +159,11 @@ struct pllb_context {
   int64_t meta_cap = 0;
   cudaEvent_t ev_meta = nullptr;    // recorded after the H2D copy of meta_host: the next call waits on it before refilling
   bool meta_pending = false;
+  // The workspace (activations, plan, meta_dev) is shared by every call on this handle: each call
+  // records ev_done on its stream when it has enqueued everything, and the next call's stream waits
+  // on it, so calls issued on different streams are ordered instead of racing on the workspace.
+  cudaEvent_t ev_done = nullptr;
+  bool done_pending = false;
   // scratch for the _host entry points
   void* io_dev = nullptr;
   int64_t io_cap = 0;
@@ -197,6 +274,8 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
               float* out_cls = nullptr) {
   const pllb_model_desc& d = c->d;
   const int H = d.hidden, I = d.intermediate;
+  NvtxRange r_chunk("pllb chunk");
+  NvtxRange r_stage("stage1: masked-copy expansion + embeddings");
   RC(launch_expand_plan(tokens, tok_off, copy_base, row_base, n_hyp, d.vocab, cls != nullptr, c->plan, s));
   const int n_layers = upto_layer < 0 ? d.num_layers : std::min(upto_layer, d.num_layers);
   // Layer-0 sharing (encoder_kernels.cu, embed_unique_kernel): the masked copies of a hypothesis
@@ -221,6 +300,7 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   // projection, LayerNorms and FFN run on the gathered masked rows only (1 row per copy
   // instead of T).  Results are identical; the reference computes and discards the rest.
   const bool prune_last = upto_layer < 0 && n_layers > 0;
+  r_stage.next("stage2: encoder");
   for (int l = 0; l < n_layers; ++l) {
     const LayerDev& L = c->layers[l];
     const bool shared_rows = share && l == 0;
@@ -251,6 +331,7 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
     RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hidden_f32, c->hidden_bf16, n_rows, I, s));
   }
   if (upto_layer >= 0) return PLLB_OK;
+  r_stage.next("stage3: head at the masked rows");
   if (cls) {
     // RescoreBert: lm_score = Linear(H, 1)(last_hidden_state[:, 0, :]) — RescoreBert/model.py:13-21.
     // The pruned last layer left the final [CLS] states in hid_c (fp32, T32 layout).
@@ -299,6 +380,19 @@ int meta_acquire(pllb_context* c) {
     PLLB_CUDA(cudaEventSynchronize(c->ev_meta));
     c->meta_pending = false;
   }
+  return PLLB_OK;
+}
+
+// Orders this call after the previous one on the same handle (no-op when both use one stream).
+int workspace_acquire(pllb_context* c, cudaStream_t s) {
+  if (c->done_pending) PLLB_CUDA(cudaStreamWaitEvent(s, c->ev_done, 0));
+  return PLLB_OK;
+}
+
+int workspace_release(pllb_context* c, cudaStream_t s) {
+  if (!c->ev_done) PLLB_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+  PLLB_CUDA(cudaEventRecord(c->ev_done, s));
+  c->done_pending = true;
   return PLLB_OK;
 }
 
@@ -356,6 +450,7 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
   }
   RC(ensure_meta(c, meta_need, s));
   RC(meta_acquire(c));
+  RC(workspace_acquire(c, s));
   for (const auto& ch : chunks) {
     int32_t* tok_off = c->meta_host + ch.meta_off;
     int32_t* copy_base = tok_off + (ch.n_hyp + 1);
@@ -389,6 +484,7 @@ int score_impl(pllb_context* c, const int32_t* hyp_tokens, const int64_t* off, i
     c->stats.tokens_expanded += ch.n_rows;
   }
   if (c->timing) { PLLB_CUDA(cudaEventRecord(c->ev_end, s)); c->have_total = true; }
+  RC(workspace_release(c, s));
   c->stats.kernel_launches += g_launch_counter - launches_before;
   return PLLB_OK;
 }
@@ -469,10 +565,10 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   RC(check_device());
   const pllb_model_desc& d = *desc;
   if (d.hidden % 256 != 0 || d.hidden < 256 || d.hidden > 1024 || d.num_heads * 64 != d.hidden ||
-      d.intermediate % 256 != 0 || d.num_layers < 0 || d.vocab < 1 || d.max_position < 3 ||
+      d.intermediate % 256 != 0 || d.num_layers < 1 || d.vocab < 1 || d.max_position < 3 ||
       (d.operand_dtype != 0 && d.operand_dtype != 1))
-    return fail(PLLB_ERR_INVALID, "unsupported model shape: need hidden in {256,512,768,1024}, head dim 64, "
-                                  "intermediate % 256 == 0");
+    return fail(PLLB_ERR_INVALID, "unsupported model shape: need num_layers >= 1, hidden in {256,512,768,1024}, "
+                                  "head dim 64, intermediate % 256 == 0");
   PLLB_CUDA(cudaSetDevice(device));
   int major = 0;
   PLLB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
@@ -543,8 +639,6 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
 
   // workspace: sized by the expanded-token budget of one chunk
   if (max_chunk_tokens <= 0) max_chunk_tokens = (int64_t)1 << 20;
-  const int64_t longest = (int64_t)(d.max_position - 2) * d.max_position;   // one max-length hypothesis
-  (void)longest;
   c->cap_rows = align_up(std::max<int64_t>(max_chunk_tokens, 1024), 128);
   c->cap_copies = c->cap_rows / 4 + 128;
   c->cap_hyps = c->cap_rows / 4 + 128;
@@ -587,6 +681,7 @@ int pllb_destroy(pllb_handle h) {
   if (h->meta_dev) cudaFree(h->meta_dev);
   if (h->meta_host) cudaFreeHost(h->meta_host);
   if (h->ev_meta) cudaEventDestroy(h->ev_meta);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
   if (h->io_dev) cudaFree(h->io_dev);
   for (auto& t : h->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   if (h->ev_begin) { cudaEventDestroy(h->ev_begin); cudaEventDestroy(h->ev_end); }
@@ -693,6 +788,7 @@ int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, in
     return fail(PLLB_ERR_OOM, "pllb_expand: input exceeds one chunk");
   RC(ensure_meta(h, 3 * (int64_t)(n_hyp + 1), s));
   RC(meta_acquire(h));
+  RC(workspace_acquire(h, s));
   int32_t* tok_off = h->meta_host;
   int32_t* copy_base = tok_off + (n_hyp + 1);
   int32_t* row_base = copy_base + (n_hyp + 1);
@@ -708,7 +804,7 @@ int pllb_expand(pllb_handle h, const int32_t* hyp_tokens, const int64_t* off, in
                         false, h->plan, s));
   RC(launch_expand_ids(hyp_tokens, d_tok_off, h->plan, (int32_t)copies, h->d.cls_id, h->d.sep_id, h->d.mask_id, out_ids,
                        out_mask_pos, out_labels, s));
-  return PLLB_OK;
+  return workspace_release(h, s);
 }
 
 int pllb_get_stats(pllb_handle h, pllb_stats* out) {
@@ -781,8 +877,7 @@ int pllb_debug_hidden(pllb_handle h, const int32_t* hyp_tokens, const int64_t* h
 int pllb_levenshtein(const int32_t* ref_cp, const int64_t* ref_off, const int32_t* hyp_cp, const int64_t* hyp_off,
                      const int32_t* pair_ref, int32_t n_pairs, int32_t max_len, int32_t* out_dist, void* stream) {
   RC(check_device());
-  const int64_t before = g_launch_counter;
-  (void)before;
+  NvtxRange r("stage4: levenshtein");
   return launch_levenshtein(ref_cp, ref_off, hyp_cp, hyp_off, pair_ref, n_pairs, max_len, out_dist, (cudaStream_t)stream);
 }
 
@@ -877,6 +972,7 @@ int pllb_rescore_sweep(const double* am, const double* lm, const int64_t* len, c
                        int32_t n_best, const double* weights, int32_t W, int32_t variant, int32_t* out_argmax,
                        int64_t* out_edit_sum, void* stream) {
   RC(check_device());
+  NvtxRange r("stage4: weight sweep");
   return launch_rescore_sweep(am, lm, len, dist, N, n_best, weights, W, variant, out_argmax, out_edit_sum,
                               (cudaStream_t)stream);
 }

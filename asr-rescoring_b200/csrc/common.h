@@ -35,6 +35,24 @@ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 
 int sm_count();   // SMs of the current device (cached)
 
+// 2-D row-major tensor [rows, cols] of `elt_bytes`-byte elements, box = [box_rows, box_cols] with
+// 128-byte swizzle (box_cols * elt_bytes must be 128).  Encoded once per distinct
+// (base, shape, box) and cached per host thread (api.cu).
+int get_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows, uint64_t cols,
+                uint32_t box_rows, uint32_t box_cols);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation and device
+template <typename K>
+inline cudaError_t opt_in_smem(K kern, int bytes) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done_dev == dev) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done_dev = dev;
+  return e;
+}
+
 // ---- GEMM (gemm_tcgen05.cu) -------------------------------------------------
 enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 0,       // out bf16 = acc + bias

@@ -48,14 +48,12 @@ constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_CN = 4;
 
-constexpr int SMEM_RED = 16;                                               // (unused)
 constexpr int SMEM_XCHG = 2 * 2 * MAX_CN * BM * 8;                         // [parity][rank*2+half][row] float2
-constexpr int SMEM_GB = 0;                                                 // gamma / beta come through the read-only L1 path
 constexpr int SMEM_BARS = 512;
 template <bool STAGED>
 constexpr int smem_total() {
-  return (STAGED ? 3 : 4) * (A_STAGE_BYTES + B_STAGE_BYTES) + (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + SMEM_RED +
-         SMEM_XCHG + SMEM_GB + SMEM_BARS + 1024;
+  return (STAGED ? 3 : 4) * (A_STAGE_BYTES + B_STAGE_BYTES) + (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + SMEM_XCHG + SMEM_BARS +
+         1024;
 }
 
 static_assert(smem_total<true>() <= 232448 && smem_total<false>() <= 232448, "shared memory budget of one CTA");
@@ -103,39 +101,6 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, f
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
                ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_mbar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-
-// tcgen05.ld 32 lanes x 32 columns straight into x[OFF .. OFF+31] (no staging registers)
-#define PLLB_X(i) "=r"(xr[OFF + (i)])
-template <int OFF, int N>
-__device__ __forceinline__ void tmem_ld_into(uint32_t taddr, uint32_t (&xr)[N]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : PLLB_X(0), PLLB_X(1), PLLB_X(2), PLLB_X(3), PLLB_X(4), PLLB_X(5), PLLB_X(6), PLLB_X(7), PLLB_X(8), PLLB_X(9),
-        PLLB_X(10), PLLB_X(11), PLLB_X(12), PLLB_X(13), PLLB_X(14), PLLB_X(15), PLLB_X(16), PLLB_X(17), PLLB_X(18),
-        PLLB_X(19), PLLB_X(20), PLLB_X(21), PLLB_X(22), PLLB_X(23), PLLB_X(24), PLLB_X(25), PLLB_X(26), PLLB_X(27),
-        PLLB_X(28), PLLB_X(29), PLLB_X(30), PLLB_X(31)
-      : "r"(taddr)
-      : "memory");
-}
-#undef PLLB_X
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -154,12 +119,6 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
 // ordered (volatile) loads: keeps ptxas from hoisting a tile's worth of parameter loads above
 // the 128-register row slice and spilling it
 __device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
@@ -167,12 +126,6 @@ __device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ float4 lds_f4_ordered(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-
 template <int CN, bool FP16, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -187,11 +140,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
   const uint32_t sEpi = smem_base + SMEM_PIPE;
-  const uint32_t sRed = sEpi + SMEM_EPI;
-  const uint32_t sXchg = sRed + SMEM_RED;
-  const uint32_t sGB = sXchg + SMEM_XCHG;
-  const uint32_t sBar = sGB + SMEM_GB;
-  float2* xchg = reinterpret_cast<float2*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_RED);   // [2][MAX_CN][128]
+  const uint32_t sXchg = sEpi + SMEM_EPI;
+  const uint32_t sBar = sXchg + SMEM_XCHG;
+  float2* xchg = reinterpret_cast<float2*>(smem_gen + SMEM_PIPE + SMEM_EPI);   // [parity][rank*2+half][row]
   const uint32_t bar_full = sBar;                         // STAGES
   const uint32_t bar_empty = bar_full + 8 * STAGES;       // STAGES
   const uint32_t bar_tfull = bar_empty + 8 * STAGES;      // 2
@@ -474,34 +425,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
-}
-
 int tmap2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt, uint64_t rows, uint64_t cols,
            uint32_t box_rows, uint32_t box_cols) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * (uint64_t)elt};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
-  return PLLB_OK;
+  return get_tmap_2d(m, base, dt, elt, rows, cols, box_rows, box_cols);
 }
 
 template <int CN, bool FP16, bool STAGED>
@@ -509,7 +435,7 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
               const LnParams& lp, int64_t tiles_m, cudaStream_t stream) {
   auto kern = gemm_ln_kernel<CN, FP16, STAGED>;
   constexpr int SMEM_TOTAL = smem_total<STAGED>();
-  PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  PLLB_CUDA(opt_in_smem(kern, SMEM_TOTAL));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_TOTAL;

@@ -23,7 +23,6 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
-#include <mutex>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -409,44 +408,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// 2-D row-major tensor [rows, cols] of `elt_bytes`-byte elements; box = [box_rows, box_cols],
-// 128-byte swizzle (box_cols * elt_bytes must be 128).
 int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows, uint64_t cols,
               uint32_t box_rows, uint32_t box_cols) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * (uint64_t)elt_bytes};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(PLLB_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string((int)r));
-  return PLLB_OK;
+  return get_tmap_2d(m, base, dt, elt_bytes, rows, cols, box_rows, box_cols);
 }
 
 template <int EPI, bool FP16, int MODE>
 int launch_epi3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
                 cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<EPI, FP16, MODE>;
-  PLLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+  PLLB_CUDA(opt_in_smem(kern, SMEM_TOTAL));
   if constexpr (MODE != 0) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

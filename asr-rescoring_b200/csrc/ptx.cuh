@@ -45,12 +45,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must trap (error the launch), never hang the GPU.
+// Bounded wait: a pipeline bug must trap (error the launch), never hang the GPU.  The bound is
+// 2^28 polls (4x the round-1 bound; far beyond any legitimate wait, even time-sliced or under
+// compute-sanitizer / cuda-gdb); -DPLLB_SPIN_LIMIT=0 compiles the check out.
+#ifndef PLLB_SPIN_LIMIT
+#define PLLB_SPIN_LIMIT (1u << 28)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if PLLB_SPIN_LIMIT
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();   // no printf here: a call site would spill every live register
+    if (++spins > PLLB_SPIN_LIMIT) __trap();   // no printf here: a call site would spill every live register
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {}
+#endif
 }
 
 // ---------------------------------------------------------------- proxies / TMA
