@@ -127,8 +127,20 @@ def run_one_epoch(config, model: PllScorer, dataloader, output_score=None, train
 
 # ---------------------------------------------------------------------------- data
 def _tokenizer(config):
-    vocab_path = getattr(config.model, "vocab_path", None)
-    return BertCharTokenizer(vocab_path) if vocab_path else SyntheticCharTokenizer()
+    """The reference always tokenises with BertTokenizer.from_pretrained("bert-base-chinese")
+    (MLM_PLL/preprocess.py:34).  Offline that vocabulary comes from ``model.vocab_path`` (or
+    $PLLB_VOCAB).  The synthetic char->id map is only meaningful for random-init weights: it is
+    allowed with ``model.random_init_seed`` and no checkpoint, and refused otherwise — a real
+    checkpoint scored with made-up ids would still write plausible-looking *_lm.json files."""
+    vocab_path = getattr(config.model, "vocab_path", None) or os.environ.get("PLLB_VOCAB")
+    if vocab_path:
+        return BertCharTokenizer(vocab_path)
+    ckpt = getattr(config, "checkpoint_path", None)
+    if (ckpt and os.path.exists(ckpt)) or getattr(config.model, "random_init_seed", None) is None:
+        raise FileNotFoundError("text input (hyps_text.json) needs the checkpoint's vocabulary: set model.vocab_path "
+                                "(or $PLLB_VOCAB) to its vocab.txt; the synthetic tokenizer is only allowed with "
+                                "model.random_init_seed and no checkpoint")
+    return SyntheticCharTokenizer()
 
 
 def load_split(path: str, num_of_data: int, config) -> Tuple[Optional[list], Dict[str, Dict[str, List[int]]]]:
@@ -137,6 +149,11 @@ def load_split(path: str, num_of_data: int, config) -> Tuple[Optional[list], Dic
     if isinstance(data, list):                       # reference row list
         return data[:num_of_data], {}
     if isinstance(data, dict) and data.get("format") == "pllb-packed-v1":
+        kind = data.get("tokenizer", "unknown")
+        ckpt = getattr(config, "checkpoint_path", None)
+        if kind == "synthetic" and ckpt and os.path.exists(ckpt):
+            raise ValueError(f"{path} was tokenised with the synthetic char->id map; it cannot be scored with the "
+                             f"checkpoint {ckpt!r} (re-run preprocess.py with PLLB_VOCAB=<vocab.txt>)")
         hyps: Dict[str, Dict[str, List[int]]] = {}
         off, tok = data["offsets"], data["tokens"]
         for i, (u, h) in enumerate(zip(data["utt_id"], data["hyp_id"])):
@@ -188,11 +205,11 @@ def score_split(config, model: PllScorer, path: str) -> dict:
     rank, world, _ = shard.dist_env()
     if rows is not None:
         output_score = skeleton_from_rows(rows)
-        if world > 1:
-            raise NotImplementedError("row-list inputs are scored on one GPU; use hyps_text / packed JSON to shard")
-        loader = set_dataloader(config.dataloader, MyDataset(rows), True)
-        return run_one_epoch(config=config, model=model, dataloader=loader, output_score=output_score,
-                             train_mode=False, do_scoring=True)
+        if world == 1:
+            loader = set_dataloader(config.dataloader, MyDataset(rows), True)
+            return run_one_epoch(config=config, model=model, dataloader=loader, output_score=output_score,
+                                 train_mode=False, do_scoring=True)
+        return _score_rows_sharded(config, model, rows, output_score, rank, world)
     utts = list(hyps.keys())
     parts = shard.lpt_partition(shard.utterance_costs([[len(t) for t in hyps[u].values()] for u in utts]), world)
     mine = [utts[i] for i in parts[rank]]
@@ -209,6 +226,36 @@ def score_split(config, model: PllScorer, path: str) -> dict:
             out[u][h] = float(full[j]) if len(toks) > 0 else 0
             j += 1
     return out
+
+
+def _score_rows_sharded(config, model: PllScorer, rows: list, output_score: dict, rank: int, world: int) -> dict:
+    """Row-list input on several GPUs: rows of one utterance are consecutive (preprocess.py emits
+    them so); the utterance segments are LPT-partitioned by their token count, every rank runs
+    run_one_epoch on its own rows, and the per-(utt, hyp) sums are gathered.  A hypothesis with
+    no rows keeps the int 0 of the skeleton (MLM_PLL/main.py:189-193), as on one GPU."""
+    seg_start, seg_utt = [], []
+    for i, row in enumerate(rows):
+        if not seg_utt or row["utt_id"] != seg_utt[-1]:
+            seg_start.append(i)
+            seg_utt.append(row["utt_id"])
+    seg_start.append(len(rows))
+    if len(set(seg_utt)) != len(seg_utt):
+        raise ValueError("row list has non-consecutive rows of one utterance; cannot shard it by utterance")
+    costs = [sum(len(r["input_ids"]) for r in rows[seg_start[j]:seg_start[j + 1]]) for j in range(len(seg_utt))]
+    mine = shard.lpt_partition(costs, world)[rank]
+    my_rows = [r for j in mine for r in rows[seg_start[j]:seg_start[j + 1]]]
+    local = {seg_utt[j]: dict(output_score[seg_utt[j]]) for j in mine}
+    loader = set_dataloader(config.dataloader, MyDataset(my_rows), True)
+    run_one_epoch(config=config, model=model, dataloader=loader, output_score=local, train_mode=False, do_scoring=True)
+    keys = [(u, h) for u, hs in output_score.items() for h in hs]
+    index = {k: i for i, k in enumerate(keys)}
+    idx = np.array([index[(u, h)] for u, hs in local.items() for h in hs], np.int64)
+    vals = np.array([float(v) for hs in local.values() for v in hs.values()], np.float64)
+    full = shard.gather_scores(vals, idx, len(keys))
+    scored = {(r["utt_id"], r["hyp_id"]) for r in rows}
+    for (u, h), v in zip(keys, full):
+        output_score[u][h] = float(v) if (u, h) in scored else 0
+    return output_score
 
 
 def pll_bert_scoring(config):

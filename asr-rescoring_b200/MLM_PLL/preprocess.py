@@ -55,12 +55,24 @@ def pack_hyps_text(hyps_text: dict, tokenizer) -> dict:
             hyp.append(hyp_id)
             tokens.extend(tokenizer.encode(sentence))
             offsets.append(len(tokens))
-    return {"format": "pllb-packed-v1", "utt_id": utt, "hyp_id": hyp, "tokens": tokens, "offsets": offsets}
+    kind = "synthetic" if isinstance(tokenizer, SyntheticCharTokenizer) else "bert-vocab"
+    return {"format": "pllb-packed-v1", "tokenizer": kind, "utt_id": utt, "hyp_id": hyp, "tokens": tokens,
+            "offsets": offsets}
 
 
 if __name__ == "__main__":
-    vocab = os.environ.get("PLLB_VOCAB")   # path to bert-base-chinese vocab.txt when available
-    bert_tokenizer = BertCharTokenizer(vocab) if vocab else SyntheticCharTokenizer()
+    # The reference fetches the bert-base-chinese vocabulary from the hub (preprocess.py:34); offline
+    # it has to be given.  The synthetic char->id map is an explicit opt-in for random-init
+    # experiments (PLLB_SYNTHETIC_TOKENIZER=1) and is recorded in the packed file, so main.py can
+    # refuse to score a real checkpoint with it.
+    vocab = os.environ.get("PLLB_VOCAB")
+    if vocab:
+        bert_tokenizer = BertCharTokenizer(vocab)
+    elif os.environ.get("PLLB_SYNTHETIC_TOKENIZER") == "1":
+        bert_tokenizer = SyntheticCharTokenizer()
+    else:
+        raise SystemExit("preprocess.py: set PLLB_VOCAB=<path to bert-base-chinese vocab.txt> "
+                         "(or PLLB_SYNTHETIC_TOKENIZER=1 for random-init experiments)")
     jobs = [
         {"task": "for_scoring", "in": "../espnet_data/alfred/train/hyps_text.json", "out": "preprocessed_data/for_scoring/train.json"},
         {"task": "for_scoring", "in": "../espnet_data/alfred/dev/hyps_text.json", "out": "preprocessed_data/for_scoring/dev.json"},

@@ -132,7 +132,14 @@ struct TimedLaunch {
 struct pllb_context {
   pllb_model_desc d{};
   int device = 0;
-  bool fp16 = false;                 // GEMM operand dtype: bf16 (default) or IEEE fp16
+  // operand types (pllb_model_desc.operand_dtype): 0 bf16 | 1 fp16 | 2 mixed (bf16 activations x
+  // fp16 weights in the encoder, all-fp16 MLM head)
+  bool fp16 = false;                 // activation buffers (hidden16, qkv, ctx, ffn) are IEEE fp16, else bf16
+  bool w_fp16 = false;               // weights are stored as fp16, else bf16
+  bool head_fp16 = false;            // the MLM head's activations (transform input / decoder input) are fp16
+  int dt = DT_BF16;                  // GemmDtype of the encoder GEMMs
+  int dt_head = DT_BF16;             // GemmDtype of the head transform + decoder
+  int dt_last = DT_BF16;             // GemmDtype of the pruned last layer's FFN2 (its 16-bit copy feeds the head)
   bool has_head = false;             // MLM head weights were supplied (PLL scoring available)
   bool fused_ln = true;              // residual + LayerNorm inside the GEMM epilogue (PLLB_FUSED_LN=0 disables)
   bool prune_q = true;               // last layer: Q projection + attention for the consumed row only (PLLB_PRUNE_Q=0 disables)
@@ -205,7 +212,7 @@ int copy_f32(pllb_context* c, float** dst, const float* src, int64_t n, cudaStre
 int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n, cudaStream_t s) {
   int rc = dev_alloc(c, dst, n);
   if (rc) return rc;
-  return launch_f32_to_bf16(src, *dst, n, c->fp16, s);
+  return launch_f32_to_bf16(src, *dst, n, c->w_fp16, s);
 }
 
 #define RC(expr)            \
@@ -215,7 +222,8 @@ int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n,
   } while (0)
 
 int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const float* bias, void* C, int64_t M, int N,
-               int K, int epi, const LseArgs* lse, cudaStream_t s) {
+               int K, int epi, const LseArgs* lse, cudaStream_t s, int dt = -1) {
+  if (dt < 0) dt = c->dt;
   TimedLaunch* tl = nullptr;
   if (c->timing) {
     if (c->timed_used == c->timed.size()) {
@@ -228,7 +236,7 @@ int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const fl
     tl->kind = kind;
     PLLB_CUDA(cudaEventRecord(tl->start, s));
   }
-  RC(launch_gemm_tcgen05(A, W, bias, C, M, N, K, epi, lse, c->fp16, s));
+  RC(launch_gemm_tcgen05(A, W, bias, C, M, N, K, epi, lse, dt, s));
   if (tl) PLLB_CUDA(cudaEventRecord(tl->stop, s));
   const double fl = 2.0 * (double)M * (double)(epi == EPI_LSE && lse ? lse->vocab : N) * (double)K;
   c->stats.gemm_flops += fl;
@@ -239,11 +247,12 @@ int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const fl
 
 // GEMM + bias + residual + LayerNorm: fused kernel, or (PLLB_FUSED_LN=0) GEMM -> fp32 -> LayerNorm kernel.
 int timed_gemm_ln(pllb_context* c, int kind, const void* A, const void* W, const float* bias, const float* g,
-                  const float* be, float* hid32, void* hid16, int64_t M, int K, cudaStream_t s) {
+                  const float* be, float* hid32, void* hid16, int64_t M, int K, cudaStream_t s, int dt = -1) {
   const int H = c->d.hidden;
+  if (dt < 0) dt = c->dt;
   if (!c->fused_ln) {
-    RC(timed_gemm(c, kind, A, W, bias, c->y_f32, M, H, K, EPI_BIAS_F32, nullptr, s));
-    return launch_residual_ln(c->y_f32, hid32, hid16, g, be, c->d.ln_eps, M, H, c->fp16, s);
+    RC(timed_gemm(c, kind, A, W, bias, c->y_f32, M, H, K, EPI_BIAS_F32, nullptr, s, dt == DT_MIXED_OUT16 ? DT_MIXED : dt));
+    return launch_residual_ln(c->y_f32, hid32, hid16, g, be, c->d.ln_eps, M, H, (dt & 4) != 0, s);
   }
   TimedLaunch* tl = nullptr;
   if (c->timing) {
@@ -257,7 +266,7 @@ int timed_gemm_ln(pllb_context* c, int kind, const void* A, const void* W, const
     tl->kind = kind;
     PLLB_CUDA(cudaEventRecord(tl->start, s));
   }
-  RC(launch_gemm_ln(A, W, bias, g, be, c->d.ln_eps, hid32, hid16, M, H, K, c->fp16, s));
+  RC(launch_gemm_ln(A, W, bias, g, be, c->d.ln_eps, hid32, hid16, M, H, K, dt, s));
   if (tl) PLLB_CUDA(cudaEventRecord(tl->stop, s));
   const double fl = 2.0 * (double)M * (double)H * (double)K;
   c->stats.gemm_flops += fl;
@@ -323,7 +332,9 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
       RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
       RC(timed_gemm_ln(c, G_AO, c->hg, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hid_c, c->t_bf16, n_copies, H, s));
       RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
-      RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hid_c, c->t_bf16, n_copies, I, s));
+      // its 16-bit copy is the MLM head's input: written in the head's operand type
+      RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hid_c, c->t_bf16, n_copies, I, s,
+                       cls ? -1 : c->dt_last));
       break;
     }
     RC(timed_gemm_ln(c, G_AO, c->ctx, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hidden_f32, c->hidden_bf16, n_rows, H, s));
@@ -340,11 +351,12 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   }
   // MLM head at the masked row of every copy only (the reference evaluates all B*T rows,
   // transformers modeling_bert.py:975, and keeps one: MLM_PLL/main.py:101).
-  if (!prune_last) RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->t_bf16, s));
-  RC(timed_gemm(c, G_HEAD, c->t_bf16, c->head_w, c->head_b, c->t_f32, n_copies, H, H, EPI_BIAS_GELU_F32, nullptr, s));
-  RC(launch_plain_ln_bf16(c->t_f32, c->hg, c->head_g, c->head_be, d.ln_eps, n_copies, H, c->fp16, s));
+  // (num_layers >= 1, so the pruned last layer always ran and t_bf16 holds the masked rows' final states)
+  RC(timed_gemm(c, G_HEAD, c->t_bf16, c->head_w, c->head_b, c->t_f32, n_copies, H, H, EPI_BIAS_GELU_F32, nullptr, s,
+                c->dt_head));
+  RC(launch_plain_ln_bf16(c->t_f32, c->hg, c->head_g, c->head_be, d.ln_eps, n_copies, H, c->head_fp16, s));
   LseArgs lse{c->plan.label, c->partials, c->label_logit, d.vocab};
-  RC(timed_gemm(c, G_DEC, c->hg, c->dec_w, c->dec_b, nullptr, n_copies, c->vocab_pad, H, EPI_LSE, &lse, s));
+  RC(timed_gemm(c, G_DEC, c->hg, c->dec_w, c->dec_b, nullptr, n_copies, c->vocab_pad, H, EPI_LSE, &lse, s, c->dt_head));
   RC(launch_lse_finish(c->partials, c->label_logit, n_copies, 2 * c->tiles_v, c->tok_logp, s));
   RC(launch_hyp_sum(c->tok_logp, copy_base, n_hyp, out_pll, out_tok_logp, s));
   return PLLB_OK;
@@ -566,7 +578,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   const pllb_model_desc& d = *desc;
   if (d.hidden % 256 != 0 || d.hidden < 256 || d.hidden > 1024 || d.num_heads * 64 != d.hidden ||
       d.intermediate % 256 != 0 || d.num_layers < 1 || d.vocab < 1 || d.max_position < 3 ||
-      (d.operand_dtype != 0 && d.operand_dtype != 1))
+      d.operand_dtype < 0 || d.operand_dtype > 2)
     return fail(PLLB_ERR_INVALID, "unsupported model shape: need num_layers >= 1, hidden in {256,512,768,1024}, "
                                   "head dim 64, intermediate % 256 == 0");
   PLLB_CUDA(cudaSetDevice(device));
@@ -577,6 +589,11 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   c->d = d;
   c->device = device;
   c->fp16 = d.operand_dtype == 1;
+  c->w_fp16 = d.operand_dtype >= 1;
+  c->head_fp16 = d.operand_dtype >= 1;
+  c->dt = d.operand_dtype == 1 ? DT_FP16 : d.operand_dtype == 2 ? DT_MIXED : DT_BF16;
+  c->dt_head = d.operand_dtype >= 1 ? DT_FP16 : DT_BF16;
+  c->dt_last = d.operand_dtype == 1 ? DT_FP16 : d.operand_dtype == 2 ? DT_MIXED_OUT16 : DT_BF16;
   if (const char* e = getenv("PLLB_FUSED_LN")) c->fused_ln = atoi(e) != 0;
   if (const char* e = getenv("PLLB_SHARE_L0")) c->share_l0 = atoi(e) != 0;
   if (const char* e = getenv("PLLB_PRUNE_Q")) c->prune_q = atoi(e) != 0;
@@ -602,9 +619,9 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
     const pllb_layer_weights& lw = w->layers[l];
     LayerDev& L = c->layers[l];
     TRY(dev_alloc(c, &L.qkv_w, (int64_t)3 * H * H));
-    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->fp16, s));
-    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->fp16, s));
-    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->w_fp16, s));
+    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->w_fp16, s));
+    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->w_fp16, s));
     TRY(dev_alloc(c, &L.qkv_b, 3 * H));
     cudaMemcpyAsync(L.qkv_b, lw.q_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(L.qkv_b + H, lw.k_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
@@ -631,7 +648,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
     TRY(copy_f32(c, &c->head_be, w->head_ln_b, H, s));
     TRY(dev_alloc(c, &c->dec_w, (int64_t)c->vocab_pad * H));
     cudaMemsetAsync(c->dec_w, 0, sizeof(__nv_bfloat16) * (size_t)c->vocab_pad * H, s);
-    TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->w_fp16, s));
     TRY(dev_alloc(c, &c->dec_b, c->vocab_pad));
     cudaMemsetAsync(c->dec_b, 0, sizeof(float) * c->vocab_pad, s);
     cudaMemcpyAsync(c->dec_b, w->decoder_b, sizeof(float) * V, cudaMemcpyDeviceToDevice, s);
@@ -856,7 +873,16 @@ int pllb_debug_gemm(const uint16_t* A, const uint16_t* W, const float* bias, voi
                     int32_t epilogue, void* stream) {
   RC(check_device());
   if (epilogue < 0 || epilogue > 3) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm: epilogue must be 0..3");
-  return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, false, (cudaStream_t)stream);
+  return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, DT_BF16, (cudaStream_t)stream);
+}
+
+int pllb_debug_gemm_dt(const uint16_t* A, const uint16_t* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                       int32_t epilogue, int32_t operand_dtype, void* stream) {
+  RC(check_device());
+  if (epilogue < 0 || epilogue > 3) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm_dt: epilogue must be 0..3");
+  if (operand_dtype < 0 || operand_dtype > 2) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm_dt: operand_dtype must be 0..2");
+  const int dt = operand_dtype == 1 ? DT_FP16 : operand_dtype == 2 ? DT_MIXED : DT_BF16;
+  return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, dt, (cudaStream_t)stream);
 }
 
 int pllb_debug_gemm_simt(const uint16_t* A, const uint16_t* W, const float* bias, void* C, int32_t M, int32_t N,

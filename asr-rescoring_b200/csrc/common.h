@@ -62,6 +62,16 @@ enum GemmEpilogue : int {
   EPI_LSE = 4              // vocab-tiled online logsumexp + label-column pick (no C output)
 };
 
+// Operand-type bits of a GEMM launch (tcgen05 kind::f16 takes the A and B formats independently):
+//   bit 0: A (activations) is IEEE fp16, else bf16      bit 1: W (weights) is fp16, else bf16
+//   bit 2: the 16-bit output is written as fp16, else bf16
+enum GemmDtype : int {
+  DT_BF16 = 0,          // bf16 x bf16 -> bf16 out
+  DT_MIXED = 2,         // bf16 activations x fp16 weights -> bf16 out
+  DT_MIXED_OUT16 = 6,   // bf16 activations x fp16 weights -> fp16 out (feeds the all-fp16 MLM head)
+  DT_FP16 = 7           // fp16 x fp16 -> fp16 out
+};
+
 struct LseArgs {
   const int32_t* labels;   // [M] label column of each row
   float2* partials;        // [M, 2 * n_tiles_n] (running max, sum of exp) per 128-column half tile
@@ -71,13 +81,13 @@ struct LseArgs {
 
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A, W bf16 row-major (K contiguous).
 // N % 256 == 0 (pad W rows with zeros), K % 64 == 0.  ldc = N.
-// fp16 = operands (and 16-bit outputs) are IEEE half instead of bf16.
+// dt: GemmDtype (DT_MIXED_OUT16 is not instantiated for this kernel).
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                        int epilogue, const LseArgs* lse, bool fp16, cudaStream_t stream);
+                        int epilogue, const LseArgs* lse, int dt, cudaStream_t stream);
 // hidden_f32 = LayerNorm(A * W^T + bias + hidden_f32) in place, hidden_16 = 16-bit copy
 // (gemm_ln_tcgen05.cu: cluster of H/256 CTAs per 128-row block, row statistics through DSMEM).
 int launch_gemm_ln(const void* A, const void* W, const float* bias, const float* gamma, const float* beta, float eps,
-                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, bool fp16, cudaStream_t stream);
+                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, int dt, cudaStream_t stream);
 int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                      int epilogue, cudaStream_t stream);
 

@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace pllb {
 
@@ -33,13 +34,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // __nv_bfloat16 throughout and reinterpreted when the handle runs in fp16 mode.
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
-  if constexpr (FP16) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  } else {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
+  return pack16x2_sat<FP16>(lo, hi);
 }
 
 // ---------------------------------------------------------------- plan
@@ -811,8 +806,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
     *reinterpret_cast<uint2*>(dst + i) = u;
   } else {
     for (int64_t j = i; j < n; ++j) {
-      if constexpr (FP16) reinterpret_cast<__half*>(dst)[j] = __float2half_rn(src[j]);
-      else dst[j] = __float2bfloat16_rn(src[j]);
+      reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)(pack16<FP16>(src[j], 0.f) & 0xffffu);
     }
   }
 }

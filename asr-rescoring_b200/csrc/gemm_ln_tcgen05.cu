@@ -71,13 +71,7 @@ struct LnParams {
 
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
-  if constexpr (FP16) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  } else {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
+  return pack16x2_sat<FP16>(lo, hi);
 }
 
 __device__ __forceinline__ uint32_t cluster_id_x() {
@@ -126,10 +120,11 @@ __device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-template <int CN, bool FP16, bool STAGED>
+template <int CN, int DT, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH16, const LnParams p) {
+  constexpr bool FP16 = (DT & 4) != 0;          // type of the 16-bit output copy
   constexpr int STAGES = STAGED ? 3 : 4;
   constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
   constexpr int SMEM_EPI = STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0;
@@ -220,7 +215,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = FP16 ? make_idesc_f16(BM, BN) : make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_16(BM, BN, (DT & 1) != 0, (DT & 2) != 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -430,10 +425,10 @@ int tmap2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt, ui
   return get_tmap_2d(m, base, dt, elt, rows, cols, box_rows, box_cols);
 }
 
-template <int CN, bool FP16, bool STAGED>
+template <int CN, int DT, bool STAGED>
 int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t16,
               const LnParams& lp, int64_t tiles_m, cudaStream_t stream) {
-  auto kern = gemm_ln_kernel<CN, FP16, STAGED>;
+  auto kern = gemm_ln_kernel<CN, DT, STAGED>;
   constexpr int SMEM_TOTAL = smem_total<STAGED>();
   PLLB_CUDA(opt_in_smem(kern, SMEM_TOTAL));
   cudaLaunchConfig_t cfg{};
@@ -448,8 +443,8 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent: as many clusters as can be co-resident (clusters must fit inside a GPC)
-  static thread_local int max_clusters[MAX_CN + 1][4] = {};
-  int& mc = max_clusters[CN][(FP16 ? 1 : 0) + (STAGED ? 2 : 0)];
+  static thread_local int max_clusters[MAX_CN + 1][16] = {};
+  int& mc = max_clusters[CN][DT + (STAGED ? 8 : 0)];
   if (mc == 0) {
     cfg.gridDim = dim3(CN * (sm_count() / CN));
     int n = 0;
@@ -470,7 +465,7 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
 }  // namespace
 
 int launch_gemm_ln(const void* A, const void* W, const float* bias, const float* gamma, const float* beta, float eps,
-                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, bool fp16, cudaStream_t stream) {
+                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, int dt, cudaStream_t stream) {
   if (M <= 0) return PLLB_OK;
   if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
@@ -484,18 +479,25 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   const int64_t tiles_m = ceil_div(M, BM);
   // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
   const bool staged = K <= H;
+#define PLLB_LN_DT(CN_, DT_)                                                                                  \
+  return staged ? launch_cn<CN_, DT_, true>(ta, tb, t16, lp, tiles_m, stream)                                 \
+                : launch_cn<CN_, DT_, false>(ta, tb, t16, lp, tiles_m, stream);
 #define PLLB_LN(CN_)                                                                                          \
   case CN_:                                                                                                   \
-    if (fp16) return staged ? launch_cn<CN_, true, true>(ta, tb, t16, lp, tiles_m, stream)                    \
-                            : launch_cn<CN_, true, false>(ta, tb, t16, lp, tiles_m, stream);                  \
-    return staged ? launch_cn<CN_, false, true>(ta, tb, t16, lp, tiles_m, stream)                             \
-                  : launch_cn<CN_, false, false>(ta, tb, t16, lp, tiles_m, stream);
+    switch (dt) {                                                                                             \
+      case DT_BF16: PLLB_LN_DT(CN_, DT_BF16)                                                                  \
+      case DT_MIXED: PLLB_LN_DT(CN_, DT_MIXED)                                                                \
+      case DT_MIXED_OUT16: PLLB_LN_DT(CN_, DT_MIXED_OUT16)                                                    \
+      case DT_FP16: PLLB_LN_DT(CN_, DT_FP16)                                                                  \
+    }                                                                                                         \
+    return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported operand dtype combination");
   switch (H / BN) {
     PLLB_LN(1)
     PLLB_LN(2)
     PLLB_LN(3)
     PLLB_LN(4)
   }
+#undef PLLB_LN_DT
 #undef PLLB_LN
   return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported hidden size");
 }

@@ -105,13 +105,7 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 // two fp32 -> one packed 16-bit pair in the operand dtype of the handle (bf16 or fp16)
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
-  if constexpr (FP16) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  } else {
-    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
-  }
+  return pack16x2_sat<FP16>(lo, hi);
 }
 
 // MC: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (same
@@ -124,12 +118,13 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
 // ring is 6 deep; accumulators for rows 0-127 / 128-255 land in the leader's / peer's TMEM.
 // Both CTAs' TMA loads complete on the leader's full barrier; the MMA's commits are multicast
 // to both CTAs (stage release, accumulator ready); both epilogues report back to the leader.
-template <int EPI, bool FP16, int MODE>
+template <int EPI, int DT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const KParams p) {
   constexpr bool MC = MODE == 1;
   constexpr bool TWO = MODE == 2;
+  constexpr bool FP16 = (DT & 4) != 0;          // type of the 16-bit output
   // TWO: 5 x 32 KiB operand stages + two staging boxes per epilogue warp; else 4 x 48 KiB + one box
   constexpr int NST = TWO ? 5 : STAGES;
   constexpr int B_BYTES = TWO ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
@@ -228,7 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && (!TWO || crank == 0)) {                 // TWO: the leader issues for the pair
       constexpr int MMA_M = TWO ? 2 * BM : BM;
-      constexpr uint32_t idesc = FP16 ? make_idesc_f16(MMA_M, BN) : make_idesc_bf16(MMA_M, BN);
+      constexpr uint32_t idesc = make_idesc_16(MMA_M, BN, (DT & 1) != 0, (DT & 2) != 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);   // epilogue drained this accumulator
@@ -413,10 +408,10 @@ int make_tmap(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt_
   return get_tmap_2d(m, base, dt, elt_bytes, rows, cols, box_rows, box_cols);
 }
 
-template <int EPI, bool FP16, int MODE>
+template <int EPI, int DT, int MODE>
 int launch_epi3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid,
                 cudaStream_t stream) {
-  auto kern = gemm_tcgen05_kernel<EPI, FP16, MODE>;
+  auto kern = gemm_tcgen05_kernel<EPI, DT, MODE>;
   PLLB_CUDA(opt_in_smem(kern, SMEM_TOTAL));
   if constexpr (MODE != 0) {
     cudaLaunchConfig_t cfg{};
@@ -439,14 +434,22 @@ int launch_epi3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c
   }
   return PLLB_OK;
 }
+template <int EPI, int DT>
+int launch_epi2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid, int mode,
+                cudaStream_t stream) {
+  if (mode == 2) return launch_epi3<EPI, DT, 2>(a, b, c, kp, grid, stream);
+  if (mode == 1) return launch_epi3<EPI, DT, 1>(a, b, c, kp, grid, stream);
+  return launch_epi3<EPI, DT, 0>(a, b, c, kp, grid, stream);
+}
 template <int EPI>
-int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid, bool fp16,
+int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const KParams& kp, int grid, int dt,
                int mode, cudaStream_t stream) {
-  if (mode == 2)
-    return fp16 ? launch_epi3<EPI, true, 2>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 2>(a, b, c, kp, grid, stream);
-  if (mode == 1)
-    return fp16 ? launch_epi3<EPI, true, 1>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 1>(a, b, c, kp, grid, stream);
-  return fp16 ? launch_epi3<EPI, true, 0>(a, b, c, kp, grid, stream) : launch_epi3<EPI, false, 0>(a, b, c, kp, grid, stream);
+  switch (dt) {
+    case DT_BF16: return launch_epi2<EPI, DT_BF16>(a, b, c, kp, grid, mode, stream);
+    case DT_MIXED: return launch_epi2<EPI, DT_MIXED>(a, b, c, kp, grid, mode, stream);
+    case DT_FP16: return launch_epi2<EPI, DT_FP16>(a, b, c, kp, grid, mode, stream);
+  }
+  return fail(PLLB_ERR_INVALID, "gemm: unsupported operand dtype combination");
 }
 
 // 0 = one CTA per tile, 1 = CTA pairs with TMA multicast of W, 2 = cta_group::2 MMA.
@@ -467,7 +470,7 @@ int pair_mode(int epilogue) {
 }  // namespace
 
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                        int epilogue, const LseArgs* lse, bool fp16, cudaStream_t stream) {
+                        int epilogue, const LseArgs* lse, int dt, cudaStream_t stream) {
   if (M <= 0) return PLLB_OK;
   if (N % BN != 0 || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm: need N % 256 == 0 and K % 64 == 0");
@@ -499,11 +502,11 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
     grid = (int)(tiles < sm_count() ? tiles : sm_count());
   }
   switch (epilogue) {
-    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, fp16, mode, stream);
-    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, fp16, mode, stream);
-    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, fp16, mode, stream);
-    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, fp16, mode, stream);
-    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, fp16, mode, stream);
+    case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, dt, mode, stream);
+    case EPI_BIAS_GELU_BF16: return launch_epi<EPI_BIAS_GELU_BF16>(ta, tb, tc, kp, grid, dt, mode, stream);
+    case EPI_BIAS_F32: return launch_epi<EPI_BIAS_F32>(ta, tb, tc, kp, grid, dt, mode, stream);
+    case EPI_BIAS_GELU_F32: return launch_epi<EPI_BIAS_GELU_F32>(ta, tb, tc, kp, grid, dt, mode, stream);
+    case EPI_LSE: return launch_epi<EPI_LSE>(ta, tb, tc, kp, grid, dt, mode, stream);
   }
   return fail(PLLB_ERR_INVALID, "gemm: unknown epilogue");
 }

@@ -21,6 +21,18 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// two fp32 -> one packed 16-bit pair (lo in bits 0-15) in the operand dtype of the handle.
+// fp16 conversions SATURATE to +-65504 (cvt.rn.satfinite, SASS F2FP.SATFINITE) instead of
+// producing inf: an activation outlier of a fine-tuned checkpoint then costs accuracy on that
+// element, not a NaN in every score that attends to it.  bf16 has fp32's exponent range.
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack16x2_sat(float lo, float hi) {
+  uint32_t r;
+  if constexpr (FP16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -241,6 +253,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // same with fp16 A/B (format code 0)
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// general form: the A format (bits 7-9) and the B format (bits 10-12) are independent fields
+// (0 = fp16, 1 = bf16), so a bf16 activation tile can be multiplied by fp16 weights.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool a_fp16, bool b_fp16) {
+  return (1u << 4) | (a_fp16 ? 0u : (1u << 7)) | (b_fp16 ? 0u : (1u << 10)) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace pllb

@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import LayerWeights, ModelDesc, Stats, Weights, check
 
 VARIANTS = {"B": 0, "A": 1, "C": 2, 0: 0, 1: 1, 2: 2}
+OPERAND_DTYPES = {"bf16": 0, "fp16": 1, "mixed": 2}   # pllb_model_desc.operand_dtype
 GEMM_KINDS = ("qkv", "attn_out", "ffn1", "ffn2", "head_transform", "decoder_lse")
 
 
@@ -78,7 +79,7 @@ class PllScorer:
             w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
         d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
                       self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id,
-                      {"bf16": 0, "fp16": 1}[operand_dtype])
+                      OPERAND_DTYPES[operand_dtype])
         self.operand_dtype = operand_dtype
         torch.cuda.synchronize(dev)
         check(self._lib.pllb_create(ctypes.byref(self._h), ctypes.byref(d), ctypes.byref(w), int(max_chunk_tokens), device))
@@ -324,16 +325,22 @@ def rescore_scores(am, lm, lens, weight, variant="B") -> np.ndarray:
     return out.cpu().numpy()
 
 
-def debug_gemm(A_bf16, W_bf16, bias_f32, epilogue: int, simt: bool = False):
-    """Test hook: C = A @ W^T + bias through the tcgen05 (or SIMT validation) kernel."""
+def debug_gemm(A_bf16, W_bf16, bias_f32, epilogue: int, simt: bool = False, operand_dtype: str = "bf16"):
+    """Test hook: C = A @ W^T + bias through the tcgen05 (or SIMT validation) kernel.
+    operand_dtype "fp16": A and W are torch.float16; "mixed": A bfloat16, W float16."""
     import torch
     lib = _lib.load()
     _lib.require_device()
     M, K = A_bf16.shape
     N = W_bf16.shape[0]
-    out = torch.empty(M, N, dtype=torch.bfloat16 if epilogue in (0, 1) else torch.float32, device=A_bf16.device)
+    out = torch.empty(M, N, dtype=A_bf16.dtype if epilogue in (0, 1) else torch.float32, device=A_bf16.device)
     stream = torch.cuda.current_stream(A_bf16.device).cuda_stream
-    fn = lib.pllb_debug_gemm_simt if simt else lib.pllb_debug_gemm
-    check(fn(ctypes.c_void_p(A_bf16.data_ptr()), ctypes.c_void_p(W_bf16.data_ptr()), ctypes.c_void_p(bias_f32.data_ptr()),
-             ctypes.c_void_p(out.data_ptr()), M, N, K, epilogue, ctypes.c_void_p(stream)))
+    args = (ctypes.c_void_p(A_bf16.data_ptr()), ctypes.c_void_p(W_bf16.data_ptr()), ctypes.c_void_p(bias_f32.data_ptr()),
+            ctypes.c_void_p(out.data_ptr()), M, N, K, epilogue)
+    if simt:
+        check(lib.pllb_debug_gemm_simt(*args, ctypes.c_void_p(stream)))
+    elif operand_dtype == "bf16":
+        check(lib.pllb_debug_gemm(*args, ctypes.c_void_p(stream)))
+    else:
+        check(lib.pllb_debug_gemm_dt(*args, OPERAND_DTYPES[operand_dtype], ctypes.c_void_p(stream)))
     return out

@@ -30,7 +30,7 @@ _PKG_PARENT = os.path.dirname(_HERE)
 if _PKG_PARENT not in sys.path:
     sys.path.insert(0, _PKG_PARENT)
 
-from asr_rescoring_b200 import engine  # noqa: E402
+from asr_rescoring_b200 import engine, shard  # noqa: E402
 from asr_rescoring_b200.util.arg_parser import ArgParser  # noqa: E402
 
 
@@ -91,19 +91,36 @@ def pair_distances(hyps, ref, n_best) -> np.ndarray:
 
 
 def sweep(am, lm, hyps, ref, config, weights=None):
-    """(weights, cer per weight, argmax [W, N]) for the whole grid."""
+    """(weights, cer per weight, argmax [W, N]) for the whole grid.
+
+    Under torchrun (an initialised process group, one process per GPU) the utterances are split
+    into contiguous blocks, one per rank: Levenshtein distances, scores and the per-utterance
+    argmax are local; the only exchanges are ONE integer all_reduce of the per-weight edit sums
+    plus the reference length (the corpus CER of rescore.py:40 is a global sum) and a gather of
+    the argmax blocks.  Integer sums are associative, so every world size gives the same CERs."""
     n_best = config.n_best
-    hyps_len = np.array(_hyps_len(hyps, n_best), np.int64)
-    am_ = np.array(am, np.float64)[:, :n_best]
-    lm_ = np.array(lm, np.float64)
     for r in ref:
         if len(r.strip()) == 0:
             raise ValueError("one or more references are empty strings")
-    total = sum(len(r.strip()) for r in ref)
-    dist = pair_distances(hyps, ref, n_best)
     weights = _grid(config) if weights is None else np.asarray(weights, np.float64)
-    argmax, edits = engine.rescore_sweep(am_, lm_, hyps_len, dist, weights, _formula(config))
-    return weights, edits.astype(np.float64) / float(total), argmax
+    rank, world = shard.active_world()
+    N = len(ref)
+    lo, hi = shard.block_range(N, rank, world)
+    hyps_l, ref_l = hyps[lo:hi], ref[lo:hi]
+    hyps_len = np.array(_hyps_len(hyps_l, n_best), np.int64).reshape(hi - lo, -1)
+    am_ = np.array(am[lo:hi], np.float64).reshape(hi - lo, -1)[:, :n_best]
+    lm_ = np.array(lm[lo:hi], np.float64).reshape(hi - lo, -1)
+    counts = np.zeros(len(weights) + 1, np.int64)
+    argmax = np.zeros((len(weights), hi - lo), np.int32)
+    if hi > lo:
+        dist = pair_distances(hyps_l, ref_l, n_best)
+        argmax, edits = engine.rescore_sweep(am_, lm_, hyps_len, dist, weights, _formula(config))
+        counts[:-1] = edits
+        counts[-1] = sum(len(r.strip()) for r in ref_l)
+    if world > 1:
+        counts = shard.reduce_counts(counts)
+        argmax = shard.gather_blocks(argmax, N, axis=1)
+    return weights, counts[:-1].astype(np.float64) / float(counts[-1]), argmax
 
 
 def find_best_weight(am, lm, hyps, ref, config):
@@ -135,9 +152,13 @@ def get_highest_score_hyp(final_score, hyps):
 if __name__ == "__main__":
     arg_parser = ArgParser()
     config = arg_parser.parse()
+    rank, world, _local = shard.init_process_group() if shard.dist_env()[1] > 1 else (0, 1, 0)
+    if world > 1:
+        import torch
+        torch.cuda.set_device(_local)
 
     logging.basicConfig(
-        filename=config.output_path + "/rescore.log",
+        filename=(config.output_path + "/rescore.log") if rank == 0 else os.devnull,
         filemode='w',
         format='%(asctime)s,%(msecs)d %(name)s %(levelname)s %(message)s',
         datefmt='%H:%M:%S',
@@ -155,12 +176,18 @@ if __name__ == "__main__":
     best_weight, best_cer = find_best_weight(dev_am, dev_lm, dev_hyps, dev_ref, config)
     logging.info("best_weight: " + str(best_weight))
     logging.info("dev cer: " + str(best_cer))
-    print("best_weight: ", best_weight)
-    print("dev cer: ", best_cer)
+    if rank == 0:
+        print("best_weight: ", best_weight)
+        print("dev cer: ", best_cer)
 
     test_am, test_lm = _load(config.test_am_path), _load(config.test_lm_path)
     test_hyps, test_ref = _load(config.test_hyps_text_path), _load(config.test_ref_text_path)
     _, test_cers, _ = sweep(test_am, test_lm, test_hyps, test_ref, config, weights=[best_weight])
     test_cer = float(test_cers[0])
     logging.info("test cer: " + str(test_cer))
-    print("test cer: ", test_cer)
+    if rank == 0:
+        print("test cer: ", test_cer)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()

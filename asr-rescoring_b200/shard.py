@@ -36,6 +36,32 @@ def lpt_partition(costs: Sequence[int], world_size: int) -> List[np.ndarray]:
     return [np.array(sorted(b), np.int64) for b in bins]
 
 
+def active_world():
+    """(rank, world_size) of the initialised default process group; (0, 1) without one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def block_range(n: int, rank: int, world: int):
+    """Contiguous [lo, hi) share of n items for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def global_hyp_index(utt_sel: Sequence[int], n_best: int) -> np.ndarray:
+    """Position of every hypothesis of the selected utterances in the utterance-major list of the
+    WHOLE workload (utterance u, candidate k -> u * n_best + k): where a rank's scores land after
+    gather_scores, whatever the partition."""
+    utt_sel = np.asarray(utt_sel, np.int64)
+    return np.repeat(utt_sel, n_best) * n_best + np.tile(np.arange(n_best, dtype=np.int64), len(utt_sel))
+
+
 def init_process_group(backend: str | None = None):
     import torch
     import torch.distributed as dist
@@ -84,6 +110,27 @@ def gather_scores(local_values: np.ndarray, local_index: np.ndarray, n_total: in
         n = int(counts[r].item())
         out[ixs[r][:n].cpu().numpy()] = vs[r][:n].cpu().numpy()
     return out
+
+
+def gather_blocks(local: np.ndarray, n_total: int, axis: int = 0) -> np.ndarray:
+    """Inverse of block_range: every rank contributes its contiguous block along `axis`; every
+    rank gets the concatenation (length n_total along that axis).  Bit-exact transport."""
+    import torch
+    import torch.distributed as dist
+    rank, world = active_world()
+    local = np.ascontiguousarray(np.moveaxis(local, axis, 0))
+    if world == 1:
+        return np.moveaxis(local, 0, axis)
+    device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    sizes = [block_range(n_total, r, world)[1] - block_range(n_total, r, world)[0] for r in range(world)]
+    assert local.shape[0] == sizes[rank], (local.shape, sizes, rank)
+    n_max = max(sizes)
+    buf = torch.zeros((n_max,) + local.shape[1:], dtype=torch.from_numpy(local[:0]).dtype, device=device)
+    buf[:local.shape[0]] = torch.from_numpy(local).to(device)
+    outs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    full = np.concatenate([outs[r][:sizes[r]].cpu().numpy() for r in range(world)], axis=0)
+    return np.moveaxis(full, 0, axis)
 
 
 def reduce_counts(counts: np.ndarray, device=None) -> np.ndarray:

@@ -567,3 +567,159 @@ def test_layer0_sharing_is_bit_identical(monkeypatch):
     for a, b in zip(res["1"][:4], res["0"][:4]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
     assert res["1"][4] < res["0"][4]                      # and it executed fewer GEMM FLOPs
+
+
+# ----------------------------------------------------------------------------- operand types
+@pytest.mark.parametrize("mode", ["fp16", "mixed"])
+def test_gemm_operand_types_vs_fp32_torch(mode):
+    """tcgen05 kind::f16 takes the A and W formats independently: fp16 x fp16 and bf16 activations x
+    fp16 weights against a plain fp32 torch matmul of the same (exactly representable) operands."""
+    import torch
+    torch.manual_seed(5)
+    M, N, K = 300, 768, 768
+    A = torch.randn(M, K, device="cuda").to(torch.float16 if mode == "fp16" else torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda") * 0.05).to(torch.float16)
+    b = torch.randn(N, device="cuda")
+    ref = A.float() @ W.float().T + b
+    out32 = engine.debug_gemm(A, W, b, 2, operand_dtype=mode)
+    assert (out32 - ref).abs().max().item() < 1e-3
+    out16 = engine.debug_gemm(A, W, b, 0, operand_dtype=mode)
+    assert out16.dtype == A.dtype
+    ulp = 2 ** -11 if mode == "fp16" else 2 ** -8
+    assert ((out16.float() - ref).abs() <= ref.abs() * ulp + 1e-3).all()
+
+
+def test_gelu_epilogue_error_bounds():
+    """The bf16-output GELU epilogue is a degree-8 minimax polynomial for erf (no MUFU, FFMA2); the
+    fp32-output one is Abramowitz-Stegun 7.1.26.  Bounds over [-6, 6] against erf in float64:
+    |err| <= 6e-5 (+ the 16-bit output rounding) and <= 1e-6."""
+    import math
+    import torch
+    M, N, K = 4096, 256, 64
+    hi = torch.linspace(-6.0, 6.0, M, device="cuda").bfloat16()
+    lo = (torch.linspace(-6.0, 6.0, M, device="cuda") - hi.float()).bfloat16()   # x = hi + lo exactly in fp32
+    A = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    A[:, 0], A[:, 1] = hi, lo
+    W = torch.zeros(N, K, device="cuda", dtype=torch.bfloat16)
+    W[:, 0] = 1.0
+    W[:, 1] = 1.0
+    b = torch.zeros(N, device="cuda")
+    x = (hi.double() + lo.double()).cpu()
+    exact = 0.5 * x * (1.0 + torch.tensor([math.erf(v / math.sqrt(2.0)) for v in x.tolist()], dtype=torch.float64))
+    out32 = engine.debug_gemm(A, W, b, 3)[:, 0].double().cpu()
+    assert (out32 - exact).abs().max().item() <= 1e-6
+    for mode, ulp in (("bf16", 2 ** -8), ("fp16", 2 ** -11)):
+        a = A if mode == "bf16" else A.to(torch.float16)
+        w = W if mode == "bf16" else W.to(torch.float16)
+        out16 = engine.debug_gemm(a, w, b, 1, operand_dtype=mode)[:, 0].double().cpu()
+        assert ((out16 - exact).abs() <= 6e-5 + exact.abs() * ulp).all(), (mode, (out16 - exact).abs().max().item())
+
+
+def _golden_pll_case(path):
+    gold = json.load(open(path))
+    lists = gold["tokens"]
+    off = np.zeros(len(lists) + 1, np.int64)
+    np.cumsum([len(t) for t in lists], out=off[1:])
+    tok = np.array([t for l in lists for t in l], np.int32)
+    return gold, tok, off, np.array(gold["pll"], np.float64)
+
+
+def test_config4_24_layers_L64_vs_reference_golden(gold_dir):
+    """BASELINE.json configs[3] shape: bert-large-shaped encoder (24 layers, H 1024), 48 hypotheses
+    of 8..64 tokens incl. four at the extremes, against the reference's own run_one_epoch
+    (tests/golden/c4_pll_golden.json, oracle/make_golden_c2.py --c4).  fp16 operands — what the c4
+    workload of bench.py declares — meet the 0.05-nat bound with a wide margin; the mixed mode
+    (bf16 activations x fp16 weights) is measured; plain bf16 does NOT meet the bound at this depth
+    and length (weight rounding alone biases a 64-token PLL by ~0.1 nat), which the test records
+    instead of hiding."""
+    gold, tok, off, ref = _golden_pll_case(os.path.join(gold_dir, "c4_pll_golden.json"))
+    L = np.diff(off)
+    assert L.max() == 64 and L.min() == 8 and len(L) >= 40 and gold["cfg"]["num_layers"] == 24
+    sd = synth.random_init_state_dict(gold["cfg"], gold["seed"])
+    err = {}
+    for mode in ("fp16", "mixed", "bf16"):
+        with engine.PllScorer(sd, gold["cfg"], operand_dtype=mode, max_chunk_tokens=1 << 16) as sc:
+            err[mode] = np.abs(sc.score_packed(tok, off) - ref)
+        print(f"c4 golden, {mode}: max |dPLL| {err[mode].max():.4f}, mean {err[mode].mean():.4f}, "
+              f"rms/sqrt(L) {np.sqrt(np.mean(err[mode] ** 2 / L)):.5f}")
+    assert err["fp16"].max() <= PLL_TOL and err["fp16"].max() <= 0.02, err["fp16"].max()
+    assert err["mixed"].max() <= 0.08 and np.mean(err["mixed"] <= PLL_TOL) >= 0.9, err["mixed"].max()
+    assert err["bf16"].max() <= 0.25, err["bf16"].max()            # bounded, but outside the 0.05-nat tolerance
+    assert err["fp16"].mean() < err["mixed"].mean() < err["bf16"].mean()
+
+
+def test_c2_2000_utterances_pll_and_one_best_vs_reference_golden(gold_dir):
+    """north_star acceptance at a size where it can be evaluated: the first n_utts >= 2000
+    utterances x 10-best of the bench workload (BASELINE.json configs[1]) against the reference's
+    own run_one_epoch (tests/golden/c2_pll_golden.npz, oracle/make_golden_c2.py): per-hypothesis
+    |dPLL| <= 0.05 nats, rescored 1-best identical on >= 99.9 % of the utterances at the weight the
+    reference's find_best_weight picks on its own scores; near-ties are counted separately."""
+    import zlib
+    g = np.load(os.path.join(gold_dir, "c2_pll_golden.npz"))
+    n_utts, n_best, ref = int(g["n_utts"]), int(g["n_best"]), g["pll"]
+    assert n_utts >= 2000 and n_best == 10 and len(ref) == n_utts * n_best
+    nb = synth.make_nbest(n_utts, n_best, seed=0)
+    tok, off = nb.packed_tokens()
+    assert zlib.crc32(tok.tobytes()) == int(g["tok_crc"]) and zlib.crc32(off.tobytes()) == int(g["off_crc"])
+    sd = synth.random_init_state_dict(synth.BERT_BASE_CHINESE, 10)
+    c = rescore_oracle.config(n_best)
+    lm_ref = ref.reshape(n_utts, n_best)
+    lens = np.array(rescore_oracle.hyps_len_of(nb.hyps, n_best), np.int64)
+    dist = oracle.levenshtein_strings([r for r in nb.refs for _ in range(n_best)], [h for hs in nb.hyps for h in hs])
+    weights = np.arange(0.0, 1.01, 0.01)
+    _, es = oracle.rescore_sweep(nb.am, lm_ref, lens, dist.reshape(n_utts, n_best), weights, 0)
+    bw = weights[int(np.argmin(es))]                                   # first strictly smallest CER (rescore.py:41-43)
+    s_ref = rescore_oracle.rescore(bw, lens, nb.am, lm_ref, c)
+    a_ref = np.argmax(s_ref, -1)
+    top2 = np.sort(s_ref, -1)[:, -2:]
+    near_tie = (top2[:, 1] - top2[:, 0]) < 0.05 / lens.max()           # a 0.05-nat PLL change could flip these
+    for mode in ("bf16", "mixed", "fp16"):
+        with engine.PllScorer(sd, synth.BERT_BASE_CHINESE, operand_dtype=mode) as sc:
+            got = sc.score_packed(tok, off)
+        err = np.abs(got - ref)
+        a_got = np.argmax(rescore_oracle.rescore(bw, lens, nb.am, got.reshape(n_utts, n_best), c), -1)
+        same = float((a_got == a_ref).mean())
+        _, es_g = oracle.rescore_sweep(nb.am, got.reshape(n_utts, n_best), lens, dist.reshape(n_utts, n_best), weights, 0)
+        print(f"c2 golden ({n_utts} utts, weight {bw:.2f}), {mode}: max |dPLL| {err.max():.4f}, mean {err.mean():.4f}, "
+              f"> 0.05: {int((err > PLL_TOL).sum())} of {len(err)}; 1-best identical {same:.5f} "
+              f"({int((a_got != a_ref).sum())} differ, {int(near_tie.sum())} near-ties); "
+              f"edit sum at that weight {int(es_g[int(np.argmin(es))])} vs {int(es.min())}")
+        assert same >= 0.999, (mode, same)
+        assert (a_got != a_ref)[~near_tie].sum() == 0, "a 1-best changed on an utterance that is not a near-tie"
+        if mode == "bf16":
+            # 7-bit-mantissa operands: sigma(dPLL) ~ 0.003 * sqrt(L), so 0.05 is a 3-4 sigma event for the
+            # longest hypotheses — rare exceedances are expected at this scale and are counted, not hidden
+            assert err.max() <= 0.08 and np.mean(err <= PLL_TOL) >= 0.9995, (err.max(), int((err > PLL_TOL).sum()))
+        else:
+            assert err.max() <= PLL_TOL, (mode, err.max())
+
+
+def test_fp16_conversions_saturate_instead_of_overflowing():
+    """One FFN unit driven to 1e5 (> 65504, the largest finite fp16): with fp16 operands the GELU
+    output saturates (cvt.rn.satfinite) and every score stays finite; with bf16 / mixed operands
+    (fp32 exponent range for activations) the scores still match the fp32 oracle.  Also LayerNorm
+    gains scaled 30x (large-magnitude activations) in fp16 mode against the oracle."""
+    cfg = synth.BERT_TINY
+    nb = synth.make_nbest(6, 3, seed=9)
+    tok, off = nb.packed_tokens(cfg["vocab"])
+    hyps = {"u": {f"hyp_{i + 1}": [int(t) for t in tok[off[i]:off[i + 1]]] for i in range(len(off) - 1)}}
+    sd = synth.random_init_state_dict(cfg, 21, perturb=True)
+    sd["bert.encoder.layer.0.intermediate.dense.bias"][7] = 1.0e5
+    ref = pll_oracle.score_hyps(sd, cfg, hyps)
+    exp = np.array([ref["u"][h] for h in hyps["u"]])
+    for mode in ("fp16", "mixed", "bf16"):
+        with engine.PllScorer(sd, cfg, operand_dtype=mode) as sc:
+            got = sc.score_packed(tok, off)
+        assert np.isfinite(got).all(), mode
+        if mode != "fp16":
+            assert np.abs(got - exp).max() <= PLL_TOL, (mode, np.abs(got - exp).max())
+    sd = synth.random_init_state_dict(cfg, 21, perturb=True)
+    for k in sd:
+        if k.startswith("bert.") and k.endswith("LayerNorm.weight"):
+            sd[k] = sd[k] * 30.0
+    ref = pll_oracle.score_hyps(sd, cfg, hyps)
+    exp = np.array([ref["u"][h] for h in hyps["u"]])
+    for mode, tol in (("fp16", 0.02), ("mixed", PLL_TOL), ("bf16", PLL_TOL)):
+        with engine.PllScorer(sd, cfg, operand_dtype=mode) as sc:
+            got = sc.score_packed(tok, off)
+        assert np.isfinite(got).all() and np.abs(got - exp).max() <= tol, (mode, np.abs(got - exp).max())

@@ -147,6 +147,80 @@ GLOO_WORKER = textwrap.dedent("""
 """)
 
 
+GLOO_STRONG_WORKER = textwrap.dedent("""
+    import json, os, sys
+    import numpy as np
+    sys.path.insert(0, os.environ["PLLB_ROOT"])
+    import torch.distributed as dist
+    from asr_rescoring_b200 import shard, synth
+    rank, world, _ = shard.init_process_group("gloo")
+    n_best = 5
+    nb = synth.make_nbest(41, n_best, seed=3)                 # odd count: ranks own different numbers of hypotheses
+    lens = [[len(h) for h in hs] for hs in nb.hyps]
+    parts = shard.lpt_partition(shard.utterance_costs(lens), world)
+    mine = parts[rank]
+    idx = shard.global_hyp_index(mine, n_best)
+    score = lambda i: -np.sqrt(i.astype(np.float64) + 1.0) * 1.7     # stands in for the PLL of global hypothesis i
+    full = shard.gather_scores(score(idx), idx, 41 * n_best)
+    # sharded sweep plumbing of rescore.py: contiguous blocks, integer all_reduce, argmax gather
+    lo, hi = shard.block_range(41, rank, world)
+    counts = shard.reduce_counts(np.array([hi - lo, sum(len(r) for r in nb.refs[lo:hi])], np.int64))
+    arg = shard.gather_blocks(np.arange(lo, hi, dtype=np.int32)[None, :].repeat(3, 0), 41, axis=1)
+    if rank == 0:
+        print(json.dumps({"ok": bool(np.array_equal(full, score(np.arange(41 * n_best)))),
+                          "sizes": [int(len(p)) for p in parts], "counts": counts.tolist(),
+                          "arg_ok": bool(np.array_equal(arg, np.arange(41, dtype=np.int32)[None, :].repeat(3, 0))),
+                          "ref_len": sum(len(r) for r in nb.refs)}))
+    dist.destroy_process_group()
+""")
+
+
+def test_gloo_world_size_2_strong_scaling_partition_and_gather(tmp_path):
+    """The N > 1 path of bench.py / MLM_PLL/main.py / rescore.py on CPU: LPT partition with unequal
+    per-rank hypothesis counts, global indices, score gather, count reduction, argmax gather."""
+    script = tmp_path / "s.py"
+    script.write_text(GLOO_STRONG_WORKER)
+    env = dict(os.environ, PLLB_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29573", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok"] and res["arg_ok"] and sum(res["sizes"]) == 41 and res["sizes"][0] != res["sizes"][1]
+    assert res["counts"] == [41, res["ref_len"]]
+
+
+def test_build_is_serialised_by_a_file_lock():
+    from asr_rescoring_b200 import build as b
+    import inspect
+    src = inspect.getsource(b.build) + inspect.getsource(b._build_locked)
+    assert "fcntl.flock" in src and "os.replace" in src
+    assert b.build() == b.LIB                                  # fresh library: returns without compiling
+
+
+def test_text_input_refuses_the_synthetic_tokenizer_with_a_real_checkpoint(tmp_path):
+    """a checkpoint scored with made-up token ids must raise, not write plausible files."""
+    import torch
+    from types import SimpleNamespace
+    from asr_rescoring_b200.MLM_PLL import main as m
+    ckpt = tmp_path / "ckpt.pt"
+    torch.save({}, ckpt)
+    cfg_ckpt = SimpleNamespace(checkpoint_path=str(ckpt), model=SimpleNamespace(bert="bert-base-chinese"))
+    with pytest.raises(FileNotFoundError):
+        m._tokenizer(cfg_ckpt)
+    cfg_none = SimpleNamespace(checkpoint_path="", model=SimpleNamespace(bert="bert-base-chinese"))
+    with pytest.raises(FileNotFoundError):
+        m._tokenizer(cfg_none)
+    cfg_rand = SimpleNamespace(checkpoint_path="", model=SimpleNamespace(bert="bert-base-chinese", random_init_seed=10))
+    assert isinstance(m._tokenizer(cfg_rand), SyntheticCharTokenizer)
+    packed = tmp_path / "p.json"
+    packed.write_text(json.dumps({"format": "pllb-packed-v1", "tokenizer": "synthetic", "utt_id": ["u"], "hyp_id": ["hyp_1"],
+                                  "tokens": [700], "offsets": [0, 1]}))
+    with pytest.raises(ValueError):
+        m.load_split(str(packed), None, cfg_ckpt)
+    assert m.load_split(str(packed), None, cfg_rand)[1] == {"u": {"hyp_1": [700]}}
+
+
 def test_gloo_world_size_2_gather_and_reduce(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(GLOO_WORKER)
@@ -239,4 +313,19 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["metric"] == "N-best PLL hypotheses/sec" and d["unit"] == "hyps/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    # baseline/_ref (the unmodified reference files, baseline/install_ref.py) is what runs when present
+    expect = "reference" if os.path.exists(os.path.join(root, "baseline", "_ref", "MLM_PLL", "main.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == expect and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+
+
+def test_bench_reference_arm_combiner_workload():
+    """--workload c5 --impl reference: the reference's find_best_weight on a reduced list."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c5",
+                          "--utts", "40", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1500:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and 0.0 <= d["best_weight"] <= 1.0 and d["dtype"] == "f64"
