@@ -57,7 +57,28 @@ model:
                                os.path.join(tmp, "score.yaml")])
         multi = {s: json.load(open(os.path.join(tmp, "result", f"{s}_lm.json"))) for s in splits}
         assert multi == one, "multi-GPU scores differ from single-GPU scores"
-        print(f"{args.gpus}-GPU output identical to 1-GPU output (bitwise)")
+        print(f"{args.gpus}-GPU *_lm.json identical to the 1-GPU files (bitwise, {sum(len(v) for v in one.values())} utterances)")
+        # the reference's row-list input (MLM_PLL/preprocess.py schema), cut mid-hypothesis by num_of_data
+        from asr_rescoring_b200.tokenizer import SyntheticCharTokenizer as _Tk
+        tk_ = _Tk()
+        for split, nb_ in splits.items():
+            rows = []
+            for u, hs in nb_.hyps_text().items():
+                for h, sent in hs.items():
+                    rows += pll_oracle.expand_rows(tk_.encode(sent), u, h)
+            json.dump(rows, open(os.path.join(tmp, f"{split}_rows.json"), "w"))
+        yaml_rows = yaml_txt.replace("_hyps_text.json", "_rows.json").replace("num_of_data: 99999999", "num_of_data: 777") \
+                            .replace(f"{tmp}/result/", f"{tmp}/result_rows/")
+        os.makedirs(os.path.join(tmp, "result_rows"))
+        open(os.path.join(tmp, "score_rows.yaml"), "w").write(yaml_rows)
+        subprocess.check_call([sys.executable, main_py, "--config", os.path.join(tmp, "score_rows.yaml")])
+        one_rows = {s: json.load(open(os.path.join(tmp, "result_rows", f"{s}_lm.json"))) for s in splits}
+        subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                               "--master-addr", "127.0.0.1", "--master-port", "29578", main_py, "--config",
+                               os.path.join(tmp, "score_rows.yaml")])
+        multi_rows = {s: json.load(open(os.path.join(tmp, "result_rows", f"{s}_lm.json"))) for s in splits}
+        assert multi_rows == one_rows, "multi-GPU row-list scores differ from single-GPU scores"
+        print(f"{args.gpus}-GPU row-list input (num_of_data cut mid-hypothesis) identical to 1 GPU (bitwise)")
     # oracle check of the dev split
     sd = synth.random_init_state_dict(cfg, 10)
     from asr_rescoring_b200.tokenizer import SyntheticCharTokenizer
@@ -93,6 +114,15 @@ output_path: "{tmp}/rescore_out"
     log = open(os.path.join(tmp, "rescore_out", "rescore.log")).read()
     assert f"best_weight: {bw}" in log and f"dev cer: {bc}" in log, (bw, bc, log[-400:])
     print("rescore.log matches the oracle's best weight and dev CER")
+    if args.gpus > 1:
+        tail = lambda t: [l.split(" INFO ")[-1] for l in t.splitlines() if "best_weight:" in l or " cer: " in l]
+        single = tail(log)
+        subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                               "--master-addr", "127.0.0.1", "--master-port", "29579", os.path.join(PKG, "rescore.py"),
+                               "--config", os.path.join(tmp, "rescore.yaml")])
+        sharded = tail(open(os.path.join(tmp, "rescore_out", "rescore.log")).read())
+        assert sharded == single and len(single) == 3, (single, sharded)
+        print(f"{args.gpus}-GPU rescore.py (sharded sweep, all_reduce of the CER counts): {sharded} — identical to 1 GPU")
 
 
 if __name__ == "__main__":
