@@ -132,11 +132,9 @@ struct TimedLaunch {
 struct pllb_context {
   pllb_model_desc d{};
   int device = 0;
-  // operand types (pllb_model_desc.operand_dtype): 0 bf16 | 1 fp16 | 2 mixed (bf16 activations x
-  // fp16 weights in the encoder, all-fp16 MLM head)
-  bool fp16 = false;                 // activation buffers (hidden16, qkv, ctx, ffn) are IEEE fp16, else bf16
-  bool w_fp16 = false;               // weights are stored as fp16, else bf16
-  bool head_fp16 = false;            // the MLM head's activations (transform input / decoder input) are fp16
+  // operand types (pllb_model_desc.operand_dtype): 0 bf16 | 1 fp16 | 2 bf16 encoder + fp16 MLM head
+  bool fp16 = false;                 // encoder activations (hidden16, qkv, ctx, ffn) and weights are IEEE fp16, else bf16
+  bool head_fp16 = false;            // the MLM head's activations and weights (transform, decoder) are fp16
   int dt = DT_BF16;                  // GemmDtype of the encoder GEMMs
   int dt_head = DT_BF16;             // GemmDtype of the head transform + decoder
   int dt_last = DT_BF16;             // GemmDtype of the pruned last layer's FFN2 (its 16-bit copy feeds the head)
@@ -212,7 +210,7 @@ int copy_f32(pllb_context* c, float** dst, const float* src, int64_t n, cudaStre
 int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n, cudaStream_t s) {
   int rc = dev_alloc(c, dst, n);
   if (rc) return rc;
-  return launch_f32_to_bf16(src, *dst, n, c->w_fp16, s);
+  return launch_f32_to_bf16(src, *dst, n, c->fp16, s);
 }
 
 #define RC(expr)            \
@@ -251,7 +249,7 @@ int timed_gemm_ln(pllb_context* c, int kind, const void* A, const void* W, const
   const int H = c->d.hidden;
   if (dt < 0) dt = c->dt;
   if (!c->fused_ln) {
-    RC(timed_gemm(c, kind, A, W, bias, c->y_f32, M, H, K, EPI_BIAS_F32, nullptr, s, dt == DT_MIXED_OUT16 ? DT_MIXED : dt));
+    RC(timed_gemm(c, kind, A, W, bias, c->y_f32, M, H, K, EPI_BIAS_F32, nullptr, s, dt == DT_BF16_OUT16 ? DT_BF16 : dt));
     return launch_residual_ln(c->y_f32, hid32, hid16, g, be, c->d.ln_eps, M, H, (dt & 4) != 0, s);
   }
   TimedLaunch* tl = nullptr;
@@ -589,11 +587,10 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   c->d = d;
   c->device = device;
   c->fp16 = d.operand_dtype == 1;
-  c->w_fp16 = d.operand_dtype >= 1;
   c->head_fp16 = d.operand_dtype >= 1;
-  c->dt = d.operand_dtype == 1 ? DT_FP16 : d.operand_dtype == 2 ? DT_MIXED : DT_BF16;
+  c->dt = d.operand_dtype == 1 ? DT_FP16 : DT_BF16;
   c->dt_head = d.operand_dtype >= 1 ? DT_FP16 : DT_BF16;
-  c->dt_last = d.operand_dtype == 1 ? DT_FP16 : d.operand_dtype == 2 ? DT_MIXED_OUT16 : DT_BF16;
+  c->dt_last = d.operand_dtype == 1 ? DT_FP16 : d.operand_dtype == 2 ? DT_BF16_OUT16 : DT_BF16;
   if (const char* e = getenv("PLLB_FUSED_LN")) c->fused_ln = atoi(e) != 0;
   if (const char* e = getenv("PLLB_SHARE_L0")) c->share_l0 = atoi(e) != 0;
   if (const char* e = getenv("PLLB_PRUNE_Q")) c->prune_q = atoi(e) != 0;
@@ -619,9 +616,9 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
     const pllb_layer_weights& lw = w->layers[l];
     LayerDev& L = c->layers[l];
     TRY(dev_alloc(c, &L.qkv_w, (int64_t)3 * H * H));
-    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->w_fp16, s));
-    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->w_fp16, s));
-    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->w_fp16, s));
+    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->fp16, s));
     TRY(dev_alloc(c, &L.qkv_b, 3 * H));
     cudaMemcpyAsync(L.qkv_b, lw.q_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(L.qkv_b + H, lw.k_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
@@ -642,13 +639,14 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   // the MLM head is optional: a RescoreBert checkpoint (BertModel + Linear) has none
   c->has_head = w->head_w && w->head_b && w->head_ln_g && w->head_ln_b && w->decoder_w && w->decoder_b;
   if (c->has_head) {
-    TRY(conv_bf16(c, &c->head_w, w->head_w, (int64_t)H * H, s));
+    TRY(dev_alloc(c, &c->head_w, (int64_t)H * H));
+    TRY(launch_f32_to_bf16(w->head_w, c->head_w, (int64_t)H * H, c->head_fp16, s));
     TRY(copy_f32(c, &c->head_b, w->head_b, H, s));
     TRY(copy_f32(c, &c->head_g, w->head_ln_g, H, s));
     TRY(copy_f32(c, &c->head_be, w->head_ln_b, H, s));
     TRY(dev_alloc(c, &c->dec_w, (int64_t)c->vocab_pad * H));
     cudaMemsetAsync(c->dec_w, 0, sizeof(__nv_bfloat16) * (size_t)c->vocab_pad * H, s);
-    TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->w_fp16, s));
+    TRY(launch_f32_to_bf16(w->decoder_w, c->dec_w, (int64_t)V * H, c->head_fp16, s));
     TRY(dev_alloc(c, &c->dec_b, c->vocab_pad));
     cudaMemsetAsync(c->dec_b, 0, sizeof(float) * c->vocab_pad, s);
     cudaMemcpyAsync(c->dec_b, w->decoder_b, sizeof(float) * V, cudaMemcpyDeviceToDevice, s);
@@ -880,8 +878,8 @@ int pllb_debug_gemm_dt(const uint16_t* A, const uint16_t* W, const float* bias, 
                        int32_t epilogue, int32_t operand_dtype, void* stream) {
   RC(check_device());
   if (epilogue < 0 || epilogue > 3) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm_dt: epilogue must be 0..3");
-  if (operand_dtype < 0 || operand_dtype > 2) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm_dt: operand_dtype must be 0..2");
-  const int dt = operand_dtype == 1 ? DT_FP16 : operand_dtype == 2 ? DT_MIXED : DT_BF16;
+  if (operand_dtype < 0 || operand_dtype > 1) return fail(PLLB_ERR_INVALID, "pllb_debug_gemm_dt: operand_dtype must be 0 or 1");
+  const int dt = operand_dtype == 1 ? DT_FP16 : DT_BF16;
   return launch_gemm_tcgen05(A, W, bias, C, M, N, K, epilogue, nullptr, dt, (cudaStream_t)stream);
 }
 

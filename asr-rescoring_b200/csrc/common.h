@@ -6,6 +6,8 @@
 
 #include <cstdio>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/pllb.h"
 
@@ -41,34 +43,39 @@ int sm_count();   // SMs of the current device (cached)
 int get_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows, uint64_t cols,
                 uint32_t box_rows, uint32_t box_cols);
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation and device
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (keyed by its address — every
+// instantiation with the same signature has the same pointer TYPE) and device.
 template <typename K>
 inline cudaError_t opt_in_smem(K kern, int bytes) {
-  static thread_local int done_dev = -1;
+  static thread_local std::vector<std::pair<const void*, int>> done;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (done_dev == dev) return cudaSuccess;
+  const void* key = reinterpret_cast<const void*>(kern);
+  for (const auto& d : done)
+    if (d.first == key && d.second == dev) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) done_dev = dev;
+  if (e == cudaSuccess) done.emplace_back(key, dev);
   return e;
 }
 
 // ---- GEMM (gemm_tcgen05.cu) -------------------------------------------------
 enum GemmEpilogue : int {
-  EPI_BIAS_BF16 = 0,       // out bf16 = acc + bias
-  EPI_BIAS_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
+  EPI_BIAS_BF16 = 0,       // out 16-bit = acc + bias
+  EPI_BIAS_GELU_BF16 = 1,  // out 16-bit = gelu_erf(acc + bias)
   EPI_BIAS_F32 = 2,        // out fp32 = acc + bias
   EPI_BIAS_GELU_F32 = 3,   // out fp32 = gelu_erf(acc + bias)
   EPI_LSE = 4              // vocab-tiled online logsumexp + label-column pick (no C output)
 };
 
-// Operand-type bits of a GEMM launch (tcgen05 kind::f16 takes the A and B formats independently):
+// Operand-type bits of a GEMM launch:
 //   bit 0: A (activations) is IEEE fp16, else bf16      bit 1: W (weights) is fp16, else bf16
 //   bit 2: the 16-bit output is written as fp16, else bf16
+// tcgen05 kind::f16 encodes the A and B formats in separate descriptor fields, but a launch
+// with A = bf16, B = fp16 dies with "illegal instruction" on B200 (measured, round 2): the two
+// operands must have the same type, so only the combinations below are instantiated.
 enum GemmDtype : int {
   DT_BF16 = 0,          // bf16 x bf16 -> bf16 out
-  DT_MIXED = 2,         // bf16 activations x fp16 weights -> bf16 out
-  DT_MIXED_OUT16 = 6,   // bf16 activations x fp16 weights -> fp16 out (feeds the all-fp16 MLM head)
+  DT_BF16_OUT16 = 4,    // bf16 x bf16 -> fp16 out (gemm_ln only: feeds the fp16 MLM head of operand mode 2)
   DT_FP16 = 7           // fp16 x fp16 -> fp16 out
 };
 
@@ -81,7 +88,7 @@ struct LseArgs {
 
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A, W bf16 row-major (K contiguous).
 // N % 256 == 0 (pad W rows with zeros), K % 64 == 0.  ldc = N.
-// dt: GemmDtype (DT_MIXED_OUT16 is not instantiated for this kernel).
+// dt: DT_BF16 or DT_FP16.
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                         int epilogue, const LseArgs* lse, int dt, cudaStream_t stream);
 // hidden_f32 = LayerNorm(A * W^T + bias + hidden_f32) in place, hidden_16 = 16-bit copy

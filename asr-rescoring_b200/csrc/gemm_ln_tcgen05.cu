@@ -486,8 +486,7 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   case CN_:                                                                                                   \
     switch (dt) {                                                                                             \
       case DT_BF16: PLLB_LN_DT(CN_, DT_BF16)                                                                  \
-      case DT_MIXED: PLLB_LN_DT(CN_, DT_MIXED)                                                                \
-      case DT_MIXED_OUT16: PLLB_LN_DT(CN_, DT_MIXED_OUT16)                                                    \
+      case DT_BF16_OUT16: PLLB_LN_DT(CN_, DT_BF16_OUT16)                                                      \
       case DT_FP16: PLLB_LN_DT(CN_, DT_FP16)                                                                  \
     }                                                                                                         \
     return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported operand dtype combination");

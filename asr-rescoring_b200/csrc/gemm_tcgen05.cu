@@ -446,7 +446,6 @@ int launch_epi(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                int mode, cudaStream_t stream) {
   switch (dt) {
     case DT_BF16: return launch_epi2<EPI, DT_BF16>(a, b, c, kp, grid, mode, stream);
-    case DT_MIXED: return launch_epi2<EPI, DT_MIXED>(a, b, c, kp, grid, mode, stream);
     case DT_FP16: return launch_epi2<EPI, DT_FP16>(a, b, c, kp, grid, mode, stream);
   }
   return fail(PLLB_ERR_INVALID, "gemm: unsupported operand dtype combination");

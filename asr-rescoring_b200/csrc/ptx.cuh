@@ -254,8 +254,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// general form: the A format (bits 7-9) and the B format (bits 10-12) are independent fields
-// (0 = fp16, 1 = bf16), so a bf16 activation tile can be multiplied by fp16 weights.
+// general form: the A format (bits 7-9) and the B format (bits 10-12) are separate fields
+// (0 = fp16, 1 = bf16), but B200 rejects kind::f16 with differing formats (illegal instruction).
 __host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, bool a_fp16, bool b_fp16) {
   return (1u << 4) | (a_fp16 ? 0u : (1u << 7)) | (b_fp16 ? 0u : (1u << 10)) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);

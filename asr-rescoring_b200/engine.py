@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import LayerWeights, ModelDesc, Stats, Weights, check
 
 VARIANTS = {"B": 0, "A": 1, "C": 2, 0: 0, 1: 1, 2: 2}
-OPERAND_DTYPES = {"bf16": 0, "fp16": 1, "mixed": 2}   # pllb_model_desc.operand_dtype
+OPERAND_DTYPES = {"bf16": 0, "fp16": 1, "bf16+fp16head": 2}   # pllb_model_desc.operand_dtype
 GEMM_KINDS = ("qkv", "attn_out", "ffn1", "ffn2", "head_transform", "decoder_lse")
 
 
@@ -327,7 +327,7 @@ def rescore_scores(am, lm, lens, weight, variant="B") -> np.ndarray:
 
 def debug_gemm(A_bf16, W_bf16, bias_f32, epilogue: int, simt: bool = False, operand_dtype: str = "bf16"):
     """Test hook: C = A @ W^T + bias through the tcgen05 (or SIMT validation) kernel.
-    operand_dtype "fp16": A and W are torch.float16; "mixed": A bfloat16, W float16."""
+    operand_dtype "fp16": A and W are torch.float16."""
     import torch
     lib = _lib.load()
     _lib.require_device()

@@ -58,9 +58,9 @@ typedef struct pllb_model_desc {
                                  tensor-core rate, 3 more mantissa bits: ~8x
                                  smaller PLL error; conversions saturate at
                                  +-65504 instead of overflowing);
-                             2 = mixed: bf16 activations (fp32 range) x fp16
-                                 weights in the encoder, all-fp16 MLM head
-                                 (~40 % of mode 0's error variance)          */
+                             2 = bf16 encoder, fp16 MLM head (transform +
+                                 decoder operands; 1 % of the FLOPs, removes
+                                 the largest single rounding site)           */
 } pllb_model_desc;
 
 /* One encoder layer; DEVICE pointers to fp32 tensors in nn.Linear layout
@@ -169,9 +169,8 @@ int pllb_get_gemm_breakdown(pllb_handle h, float* ms6, double* flops6);
  * N % 256 == 0, K % 64 == 0. */
 int pllb_debug_gemm(const uint16_t* A, const uint16_t* W, const float* bias, void* C,
                     int32_t M, int32_t N, int32_t K, int32_t epilogue, void* stream);
-/* Same with an explicit operand type (pllb_model_desc.operand_dtype codes): 0 = A and W bf16,
- * 1 = A and W IEEE fp16, 2 = A bf16 x W fp16 (tcgen05 kind::f16 takes the two formats
- * independently); 16-bit outputs are written in A's type. */
+/* Same with an explicit operand type: 0 = A and W bf16, 1 = A and W IEEE fp16 (raw uint16);
+ * 16-bit outputs are written in the operand type. */
 int pllb_debug_gemm_dt(const uint16_t* A, const uint16_t* W, const float* bias, void* C,
                        int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t operand_dtype, void* stream);
 /* Same arithmetic through the plain SIMT validation kernel (slow). */

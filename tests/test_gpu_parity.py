@@ -570,23 +570,22 @@ def test_layer0_sharing_is_bit_identical(monkeypatch):
 
 
 # ----------------------------------------------------------------------------- operand types
-@pytest.mark.parametrize("mode", ["fp16", "mixed"])
-def test_gemm_operand_types_vs_fp32_torch(mode):
-    """tcgen05 kind::f16 takes the A and W formats independently: fp16 x fp16 and bf16 activations x
-    fp16 weights against a plain fp32 torch matmul of the same (exactly representable) operands."""
+def test_gemm_fp16_operands_vs_fp32_torch():
+    """kind::f16 with IEEE-half operands against a plain fp32 torch matmul of the same (exactly
+    representable) operands.  (A = bf16 with W = fp16 is not a usable combination: the descriptor
+    has separate format fields, but B200 answers "illegal instruction" — measured in round 2.)"""
     import torch
     torch.manual_seed(5)
     M, N, K = 300, 768, 768
-    A = torch.randn(M, K, device="cuda").to(torch.float16 if mode == "fp16" else torch.bfloat16)
+    A = torch.randn(M, K, device="cuda").to(torch.float16)
     W = (torch.randn(N, K, device="cuda") * 0.05).to(torch.float16)
     b = torch.randn(N, device="cuda")
     ref = A.float() @ W.float().T + b
-    out32 = engine.debug_gemm(A, W, b, 2, operand_dtype=mode)
+    out32 = engine.debug_gemm(A, W, b, 2, operand_dtype="fp16")
     assert (out32 - ref).abs().max().item() < 1e-3
-    out16 = engine.debug_gemm(A, W, b, 0, operand_dtype=mode)
-    assert out16.dtype == A.dtype
-    ulp = 2 ** -11 if mode == "fp16" else 2 ** -8
-    assert ((out16.float() - ref).abs() <= ref.abs() * ulp + 1e-3).all()
+    out16 = engine.debug_gemm(A, W, b, 0, operand_dtype="fp16")
+    assert out16.dtype == torch.float16
+    assert ((out16.float() - ref).abs() <= ref.abs() * 2 ** -11 + 1e-3).all()
 
 
 def test_gelu_epilogue_error_bounds():
@@ -628,8 +627,8 @@ def test_config4_24_layers_L64_vs_reference_golden(gold_dir):
     """BASELINE.json configs[3] shape: bert-large-shaped encoder (24 layers, H 1024), 48 hypotheses
     of 8..64 tokens incl. four at the extremes, against the reference's own run_one_epoch
     (tests/golden/c4_pll_golden.json, oracle/make_golden_c2.py --c4).  fp16 operands — what the c4
-    workload of bench.py declares — meet the 0.05-nat bound with a wide margin; the mixed mode
-    (bf16 activations x fp16 weights) is measured; plain bf16 does NOT meet the bound at this depth
+    workload of bench.py declares — meet the 0.05-nat bound with a wide margin; bf16 with the fp16
+    head is measured; plain bf16 does NOT meet the bound at this depth
     and length (weight rounding alone biases a 64-token PLL by ~0.1 nat), which the test records
     instead of hiding."""
     gold, tok, off, ref = _golden_pll_case(os.path.join(gold_dir, "c4_pll_golden.json"))
@@ -637,15 +636,15 @@ def test_config4_24_layers_L64_vs_reference_golden(gold_dir):
     assert L.max() == 64 and L.min() == 8 and len(L) >= 40 and gold["cfg"]["num_layers"] == 24
     sd = synth.random_init_state_dict(gold["cfg"], gold["seed"])
     err = {}
-    for mode in ("fp16", "mixed", "bf16"):
+    for mode in ("fp16", "bf16+fp16head", "bf16"):
         with engine.PllScorer(sd, gold["cfg"], operand_dtype=mode, max_chunk_tokens=1 << 16) as sc:
             err[mode] = np.abs(sc.score_packed(tok, off) - ref)
         print(f"c4 golden, {mode}: max |dPLL| {err[mode].max():.4f}, mean {err[mode].mean():.4f}, "
               f"rms/sqrt(L) {np.sqrt(np.mean(err[mode] ** 2 / L)):.5f}")
     assert err["fp16"].max() <= PLL_TOL and err["fp16"].max() <= 0.02, err["fp16"].max()
-    assert err["mixed"].max() <= 0.08 and np.mean(err["mixed"] <= PLL_TOL) >= 0.9, err["mixed"].max()
-    assert err["bf16"].max() <= 0.25, err["bf16"].max()            # bounded, but outside the 0.05-nat tolerance
-    assert err["fp16"].mean() < err["mixed"].mean() < err["bf16"].mean()
+    for mode in ("bf16+fp16head", "bf16"):                          # bounded, but outside the 0.05-nat tolerance
+        assert err[mode].max() <= 0.25, (mode, err[mode].max())
+    assert err["fp16"].mean() < err["bf16+fp16head"].mean() <= err["bf16"].mean() * 1.05
 
 
 def test_c2_2000_utterances_pll_and_one_best_vs_reference_golden(gold_dir):
@@ -657,7 +656,7 @@ def test_c2_2000_utterances_pll_and_one_best_vs_reference_golden(gold_dir):
     import zlib
     g = np.load(os.path.join(gold_dir, "c2_pll_golden.npz"))
     n_utts, n_best, ref = int(g["n_utts"]), int(g["n_best"]), g["pll"]
-    assert n_utts >= 2000 and n_best == 10 and len(ref) == n_utts * n_best
+    assert n_utts >= int(os.environ.get("PLLB_C2_GOLDEN_MIN_UTTS", "2000")) and n_best == 10 and len(ref) == n_utts * n_best
     nb = synth.make_nbest(n_utts, n_best, seed=0)
     tok, off = nb.packed_tokens()
     assert zlib.crc32(tok.tobytes()) == int(g["tok_crc"]) and zlib.crc32(off.tobytes()) == int(g["off_crc"])
@@ -673,7 +672,7 @@ def test_c2_2000_utterances_pll_and_one_best_vs_reference_golden(gold_dir):
     a_ref = np.argmax(s_ref, -1)
     top2 = np.sort(s_ref, -1)[:, -2:]
     near_tie = (top2[:, 1] - top2[:, 0]) < 0.05 / lens.max()           # a 0.05-nat PLL change could flip these
-    for mode in ("bf16", "mixed", "fp16"):
+    for mode in ("bf16", "bf16+fp16head", "fp16"):
         with engine.PllScorer(sd, synth.BERT_BASE_CHINESE, operand_dtype=mode) as sc:
             got = sc.score_packed(tok, off)
         err = np.abs(got - ref)
@@ -696,8 +695,8 @@ def test_c2_2000_utterances_pll_and_one_best_vs_reference_golden(gold_dir):
 
 def test_fp16_conversions_saturate_instead_of_overflowing():
     """One FFN unit driven to 1e5 (> 65504, the largest finite fp16): with fp16 operands the GELU
-    output saturates (cvt.rn.satfinite) and every score stays finite; with bf16 / mixed operands
-    (fp32 exponent range for activations) the scores still match the fp32 oracle.  Also LayerNorm
+    output saturates (cvt.rn.satfinite) and every score stays finite; with a bf16 encoder (fp32
+    exponent range for activations) the scores still match the fp32 oracle.  Also LayerNorm
     gains scaled 30x (large-magnitude activations) in fp16 mode against the oracle."""
     cfg = synth.BERT_TINY
     nb = synth.make_nbest(6, 3, seed=9)
@@ -707,7 +706,7 @@ def test_fp16_conversions_saturate_instead_of_overflowing():
     sd["bert.encoder.layer.0.intermediate.dense.bias"][7] = 1.0e5
     ref = pll_oracle.score_hyps(sd, cfg, hyps)
     exp = np.array([ref["u"][h] for h in hyps["u"]])
-    for mode in ("fp16", "mixed", "bf16"):
+    for mode in ("fp16", "bf16+fp16head", "bf16"):
         with engine.PllScorer(sd, cfg, operand_dtype=mode) as sc:
             got = sc.score_packed(tok, off)
         assert np.isfinite(got).all(), mode
@@ -719,7 +718,7 @@ def test_fp16_conversions_saturate_instead_of_overflowing():
             sd[k] = sd[k] * 30.0
     ref = pll_oracle.score_hyps(sd, cfg, hyps)
     exp = np.array([ref["u"][h] for h in hyps["u"]])
-    for mode, tol in (("fp16", 0.02), ("mixed", PLL_TOL), ("bf16", PLL_TOL)):
+    for mode, tol in (("fp16", 0.02), ("bf16+fp16head", PLL_TOL), ("bf16", PLL_TOL)):
         with engine.PllScorer(sd, cfg, operand_dtype=mode) as sc:
             got = sc.score_packed(tok, off)
         assert np.isfinite(got).all() and np.abs(got - exp).max() <= tol, (mode, np.abs(got - exp).max())

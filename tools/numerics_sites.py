@@ -4,7 +4,7 @@ Every GEMM operand of the kernels is rounded to the operand dtype at these sites
   w      weights of all GEMMs             x_qkv  LayerNorm output feeding QKV
   qkv    Q/K/V as stored for attention    ctx    attention output feeding the output projection
   x_ff1  LayerNorm output feeding FFN1    ffn    GELU output feeding FFN2
-  head   transform input + decoder input (and their weights are under `w`)
+  head   transform input + decoder input (their weights are under `w`, or `w_head` when given)
 With ONE site rounded to bf16 and the rest exact, the spread of (PLL - fp32 PLL) over hypotheses
 gives that site's share of the error variance.
     python tools/numerics_sites.py [n_utts] [base|large]
@@ -34,7 +34,8 @@ def logits(sd, cfg, ids, mpos, dts):
     dh = H // NH
     eps = 1e-12
     ln = lambda x, p: F.layer_norm(x, (H,), sd[p + ".weight"], sd[p + ".bias"], eps)
-    lin = lambda x, p, site: F.linear(rnd(x, dts.get(site)), rnd(sd[p + ".weight"], dts.get("w")), sd[p + ".bias"])
+    wdt = lambda site: dts.get("w_head", dts.get("w")) if site == "head" else dts.get("w")
+    lin = lambda x, p, site: F.linear(rnd(x, dts.get(site)), rnd(sd[p + ".weight"], wdt(site)), sd[p + ".bias"])
     x = (sd["bert.embeddings.word_embeddings.weight"][ids] + sd["bert.embeddings.token_type_embeddings.weight"][0]
          + sd["bert.embeddings.position_embeddings.weight"][torch.arange(T)])
     x = ln(x, "bert.embeddings.LayerNorm")
@@ -51,7 +52,7 @@ def logits(sd, cfg, ids, mpos, dts):
     t = F.gelu(lin(hm, "cls.predictions.transform.dense", "head"))
     t = F.layer_norm(t, (H,), sd["cls.predictions.transform.LayerNorm.weight"],
                      sd["cls.predictions.transform.LayerNorm.bias"], eps)
-    return F.linear(rnd(t, dts.get("head")), rnd(sd["cls.predictions.decoder.weight"], dts.get("w")), sd["cls.predictions.bias"])
+    return F.linear(rnd(t, dts.get("head")), rnd(sd["cls.predictions.decoder.weight"], wdt("head")), sd["cls.predictions.bias"])
 
 
 @torch.no_grad()
@@ -76,9 +77,11 @@ if __name__ == "__main__":
         modes[f"only {s} bf16"] = {s: bf}
     modes["fp16 act, bf16 w"] = {**{s: hf for s in SITES}, "w": bf}
     modes["bf16 act, fp16 head"] = {**{s: bf for s in SITES}, "head": hf}
-    modes["mixed: bf16 act, fp16 w+head"] = {**{s: bf for s in SITES}, "head": hf, "w": hf}
+    # not runnable on B200 (kind::f16 rejects A = bf16 with B = fp16: illegal instruction), kept for the record
+    modes["(bf16 act x fp16 w, fp16 head)"] = {**{s: bf for s in SITES}, "head": hf, "w": hf}
+    modes["bf16 encoder + fp16 head"] = {**{s: bf for s in SITES}, "head": hf, "w_head": hf}     # operand mode 2
     if os.environ.get("SITES_FEW"):
-        modes = {k: v for k, v in modes.items() if k in ("all bf16", "all fp16", "mixed: bf16 act, fp16 w+head")}
+        modes = {k: v for k, v in modes.items() if k in ("all bf16", "all fp16", "bf16 encoder + fp16 head")}
     t0 = time.time()
     Ls, errs = [], {m: [] for m in modes}
     for h in range(len(off) - 1):
