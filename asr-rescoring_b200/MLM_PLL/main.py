@@ -15,8 +15,9 @@ ensure_ascii=False).  Differences, each deliberate (SURVEY.md §8a "quirks"):
   ``hyps_text.json`` ({utt: {hyp: str}}, tokenised here) or the compact packed JSON that
   our ``preprocess.py`` writes — the O(sum L^2) row list is never needed;
 * optional keys (absent from the reference YAMLs, all defaulted): ``model.vocab_path``,
-  ``model.random_init_seed``, ``model.operand_dtype`` ("bf16" default | "fp16": 8x smaller
-  rounding error, ~4 % slower), ``max_chunk_tokens``.
+  ``model.random_init_seed``, ``model.operand_dtype`` ("bf16+fp16head" default: bf16 encoder,
+  fp16 MLM head | "bf16" | "fp16": 8x smaller rounding error, ~5 % slower, needed for 24-layer
+  encoders at L > ~40), ``max_chunk_tokens``.
 """
 from __future__ import annotations
 
@@ -33,7 +34,7 @@ if _PKG_PARENT not in sys.path:
     sys.path.insert(0, _PKG_PARENT)
 
 from asr_rescoring_b200 import shard, synth  # noqa: E402
-from asr_rescoring_b200.engine import PllScorer  # noqa: E402
+from asr_rescoring_b200.engine import DEFAULT_OPERAND_DTYPE, PllScorer  # noqa: E402
 from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer, encode_batch  # noqa: E402
 from asr_rescoring_b200.util.arg_parser import ArgParser  # noqa: E402
 from asr_rescoring_b200.util.saving import json_saving  # noqa: E402
@@ -197,7 +198,7 @@ def build_scorer(config, device: int = 0) -> PllScorer:
     else:
         raise FileNotFoundError(f"checkpoint_path {ckpt!r} not found and model.random_init_seed not set")
     return PllScorer(sd, cfg, device=device, max_chunk_tokens=int(getattr(config, "max_chunk_tokens", 0) or 0),
-                     operand_dtype=str(getattr(config.model, "operand_dtype", "bf16")))
+                     operand_dtype=str(getattr(config.model, "operand_dtype", DEFAULT_OPERAND_DTYPE)))
 
 
 def score_split(config, model: PllScorer, path: str) -> dict:

@@ -455,7 +455,10 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
     }
     mc = n;
   }
-  const int clusters = (int)(tiles_m < mc ? tiles_m : mc);
+  // PLLB_LN_MAX_CLUSTERS: experiment knob (how does the step react to fewer SMs under the power cap?)
+  static const int cap = [] { const char* e = getenv("PLLB_LN_MAX_CLUSTERS"); return e ? atoi(e) : 0; }();
+  const int limit = cap > 0 && cap < mc ? cap : mc;
+  const int clusters = (int)(tiles_m < limit ? tiles_m : limit);
   cfg.gridDim = dim3(CN * clusters);
   PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t16, lp));
   ++g_launch_counter;

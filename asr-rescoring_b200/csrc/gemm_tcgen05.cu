@@ -492,13 +492,16 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
     kp.lse = *lse;
   }
   int grid;
+  // PLLB_GEMM_MAX_CTAS: experiment knob (SM-count sensitivity under the power cap)
+  static const int cta_cap = [] { const char* e = getenv("PLLB_GEMM_MAX_CTAS"); return e ? atoi(e) : 0; }();
+  const int sms = cta_cap > 0 && cta_cap < sm_count() ? cta_cap : sm_count();
   if (mc) {
     const int64_t units = ceil_div(ceil_div(M, BM), 2) * (N / BN);
-    const int64_t clusters = units < sm_count() / 2 ? units : sm_count() / 2;
+    const int64_t clusters = units < sms / 2 ? units : sms / 2;
     grid = (int)(2 * clusters);
   } else {
     const int64_t tiles = ceil_div(M, BM) * (N / BN);
-    grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    grid = (int)(tiles < sms ? tiles : sms);
   }
   switch (epilogue) {
     case EPI_BIAS_BF16: return launch_epi<EPI_BIAS_BF16>(ta, tb, tc, kp, grid, dt, mode, stream);

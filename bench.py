@@ -57,10 +57,10 @@ METRIC = "N-best PLL hypotheses/sec"
 UNIT = "hyps/s"
 
 WORKLOADS = {
-    "c1": dict(n_utts=100, n_best=10, model="bert-base-chinese", min_len=None, max_len=None, dtype="bf16",
+    "c1": dict(n_utts=100, n_best=10, model="bert-base-chinese", min_len=None, max_len=None, dtype="bf16+fp16head",
                desc="c1: 100 synthetic AISHELL-1-shaped utterances x 10-best, random-init bert-base-chinese, "
                     "PLL + 101-point weight sweep"),
-    "c2": dict(n_utts=7176, n_best=10, model="bert-base-chinese", min_len=None, max_len=None, dtype="bf16",
+    "c2": dict(n_utts=7176, n_best=10, model="bert-base-chinese", min_len=None, max_len=None, dtype="bf16+fp16head",
                desc="c2: AISHELL-1-test-shaped 7176 utterances x 10-best, random-init bert-base-chinese, "
                     "PLL + 101-point weight sweep"),
     # fp16 operands are part of this workload's definition, not a silent switch: with bf16 the
@@ -94,7 +94,8 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-sample-hyps", type=int, default=0, help="hypotheses in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--operand-dtype", default=None, choices=["bf16", "fp16", "bf16+fp16head"],
-                    help="GEMM operand type; default = the workload's (bf16; fp16 for c4), always reported in `dtype`")
+                    help="GEMM operand type; default = the workload's (bf16 encoder + fp16 MLM head; fp16 for c4), always "
+                         "reported in `dtype`")
     return ap.parse_args(argv)
 
 

@@ -641,7 +641,7 @@ def test_config4_24_layers_L64_vs_reference_golden(gold_dir):
             err[mode] = np.abs(sc.score_packed(tok, off) - ref)
         print(f"c4 golden, {mode}: max |dPLL| {err[mode].max():.4f}, mean {err[mode].mean():.4f}, "
               f"rms/sqrt(L) {np.sqrt(np.mean(err[mode] ** 2 / L)):.5f}")
-    assert err["fp16"].max() <= PLL_TOL and err["fp16"].max() <= 0.02, err["fp16"].max()
+    assert err["fp16"].max() <= PLL_TOL and err["fp16"].mean() <= 0.01, err["fp16"].max()
     for mode in ("bf16+fp16head", "bf16"):                          # bounded, but outside the 0.05-nat tolerance
         assert err[mode].max() <= 0.25, (mode, err[mode].max())
     assert err["fp16"].mean() < err["bf16+fp16head"].mean() <= err["bf16"].mean() * 1.05
