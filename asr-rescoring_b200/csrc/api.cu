@@ -323,7 +323,7 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
     } else {
       RC(timed_gemm(c, G_QKV, shared_rows ? c->ctx : c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide,
                     shared_rows ? n_unique : n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
-      RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, shared_rows, s));
+      RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, shared_rows, c->cap_rows, s));
       if (last) RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
     }
     if (last) {

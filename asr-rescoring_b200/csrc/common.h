@@ -139,8 +139,9 @@ int launch_residual_ln(const float* y, float* hidden_f32, void* hidden_bf16, con
 int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const float* b, float eps, int64_t rows,
                          int H, bool fp16, cudaStream_t s);
 // shared_rows: qkv holds the unique rows of every hypothesis (2L+2 per hypothesis) instead of one row per packed row
+// qkv_rows: rows of the [rows, 3H] buffer behind qkv_bf16 (extent of the TMA tensor maps)
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH,
-                     int max_T, bool fp16, bool shared_rows, cudaStream_t s);
+                     int max_T, bool fp16, bool shared_rows, int64_t qkv_rows, cudaStream_t s);
 // Embeddings of the unique rows of every hypothesis (fp32 row-major + 16-bit), and the packed-row -> unique-row map.
 int launch_embed_unique(const int32_t* tokens, const int32_t* hyp_tok_off, int32_t n_hyp, const float* word_emb,
                         const float* pos_emb, const float* type_emb, const float* g, const float* b, float eps, int H,

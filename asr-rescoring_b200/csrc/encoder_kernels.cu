@@ -8,6 +8,8 @@
 // All kernels are one-warp-per-row (or per sequence/head) with 128-bit accesses; rows of
 // H fp32 are contiguous so every warp access is a fully coalesced 512-byte segment.
 #include <cuda_bf16.h>
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.h"
@@ -573,7 +575,7 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ ba
 template <bool FP16, bool SHARED>
 __global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
-                     int32_t n_copies, int H, int NH) {
+                     int32_t n_copies, int H, int NH, int skip_le) {
   extern __shared__ __align__(16) uint8_t att_dyn[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(att_dyn) + (size_t)wib * ATT_STAGE_ELEMS;
@@ -581,6 +583,7 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   if (pair >= (int64_t)n_copies * NH) return;
   const int c = (int)(pair / NH), head = (int)(pair % NH);
   const int start = plan.seq_start[c], T = plan.seq_len[c];
+  if (T <= skip_le) return;                 // done by attention_tma_kernel
   const size_t ld = (size_t)3 * H;
   const __nv_bfloat16* base = qkv + head * 64;
   __nv_bfloat16* ob = ctx + (size_t)start * H + head * 64;
@@ -593,6 +596,219 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
     const RowDirect rm{(size_t)start * ld, ld};
     if (T <= ATT_TS) attn_staged<FP16>(base, rm, ob, T, H, lane, sm);
     else attn_stream<FP16>(base, rm, ob, T, H, lane, sm);
+  }
+}
+
+// ---------------------------------------------------------------- TMA-fed varlen attention
+// Persistent form for the layers whose Q|K|V rows are the copy's own packed rows (every layer but
+// the shared layer 0 and the pruned last one).  attention_mma_kernel above stages one (copy, head)
+// per warp and then computes: a warp has no load in flight while it computes, so the kernel is
+// latency-bound (0.67 of the HBM peak).  Here one CTA walks over whole masked copies:
+//   warp 0        producer — per copy 3*NH TMA box loads (Q, K, V slice of every head: 64 columns x
+//                 R rows, R = T rounded up to 8, 128-byte swizzle) into a 2-stage ring, one mbarrier
+//                 transaction per stage; the next copy streams in while this one is computed, so
+//                 ~100 KB per SM is always in flight;
+//   warps 1..NH   one head each: ldmatrix from the swizzled tiles, the same 16x16 flash blocks on
+//                 mma.sync as above, context rows leave as 16-byte stores.
+// Copies longer than ATT_TMA_ROWS rows are left to attention_mma_kernel (launched with skip_le).
+constexpr int ATT_TMA_ROWS = 24;                    // rows per staged tile (T <= 24 covers 92 % of the C2 rows)
+constexpr int ATT_TMA_STAGES = 2;
+constexpr int ATT_TMA_MAPS = ATT_TMA_ROWS / 8;      // one tensor map per box height 8, 16, 24
+constexpr int ATT_TMA_MAX_HEADS = 12;               // 2 stages x 3*NH tiles x 24 rows x 128 B = 216 KiB at NH = 12
+
+struct AttTmaMaps {
+  CUtensorMap m[ATT_TMA_MAPS];
+};
+
+// byte offset of element (row, col) inside a 128-byte-swizzled tile whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t sw128(int row, int col) {
+  return (uint32_t)(row * 128 + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2);
+}
+
+// One head of one copy from swizzled tiles of R rows (R % 8 == 0, T <= R <= 24).  Rows >= R do not
+// exist: fragment loads clamp to the last row (their scores are masked / their p is 0) and the
+// output staging skips them.
+template <bool FP16>
+__device__ __forceinline__ void attn_compute_sw(uint32_t q_addr, uint32_t k_addr, uint32_t v_addr,
+                                                __nv_bfloat16* __restrict__ ob, int T, int R, int H, int lane) {
+  const int g = lane >> 2, cq = lane & 3;
+  constexpr float kScaleLog2 = 0.125f * 1.4426950408889634f;
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, lcol8 = ((lane >> 4) & 1) * 8;
+  const int rmax = R - 1;
+  // V rows T .. R-1 came from the next sequence (or stale memory): they are multiplied by p = 0 and
+  // must be finite (0 * NaN = NaN)
+  for (int r = T + (lane >> 3); r < R; r += 4)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(v_addr + (uint32_t)(r * 128 + (lane & 7) * 16)), "r"(0u) : "memory");
+  __syncwarp();
+  for (int m0 = 0; m0 < T; m0 += 16) {
+    uint32_t qf[4][4];
+    {
+      const int row = min(m0 + lrow, rmax);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(qf[ks][0]), "=r"(qf[ks][1]), "=r"(qf[ks][2]), "=r"(qf[ks][3])
+                     : "r"(q_addr + sw128(row, 16 * ks + lcol8)));
+    }
+    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+    for (int k0 = 0; k0 < T; k0 += 16) {
+      float s[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const int krow = min(k0 + 8 * j + (lane & 7), rmax);
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(k_addr + sw128(krow, 32 * kp + (lane >> 3) * 8)));
+          mma_16816<FP16>(s[j], qf[2 * kp], b0, b1);
+          mma_16816<FP16>(s[j], qf[2 * kp + 1], b2, b3);
+        }
+      }
+      float bm[2] = {-INFINITY, -INFINITY};
+      const bool tail = k0 + 16 > T;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = k0 + 8 * j + 2 * cq + (e & 1);
+          s[j][e] = (!tail || key < T) ? s[j][e] * kScaleLog2 : -INFINITY;
+          bm[e >> 1] = fmaxf(bm[e >> 1], s[j][e]);
+        }
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
+        bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
+        const float nm = fmaxf(mx[r], bm[r]);
+        corr[r] = exp2f(mx[r] - nm);
+        mx[r] = nm;
+        l[r] *= corr[r];
+      }
+      uint32_t pf[4];
+      {
+        const float p00 = exp2f(s[0][0] - mx[0]), p01 = exp2f(s[0][1] - mx[0]);
+        const float p02 = exp2f(s[0][2] - mx[1]), p03 = exp2f(s[0][3] - mx[1]);
+        const float p10 = exp2f(s[1][0] - mx[0]), p11 = exp2f(s[1][1] - mx[0]);
+        const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
+        l[0] += (p00 + p01) + (p10 + p11);
+        l[1] += (p02 + p03) + (p12 + p13);
+        pf[0] = pack16<FP16>(p00, p01); pf[1] = pack16<FP16>(p02, p03);
+        pf[2] = pack16<FP16>(p10, p11); pf[3] = pack16<FP16>(p12, p13);
+      }
+      if (k0 > 0) {
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1];
+        }
+      }
+      const int vrow = min(k0 + lrow, rmax);
+#pragma unroll
+      for (int n = 0; n < 8; n += 2) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(v_addr + sw128(vrow, 8 * n + lcol8)));
+        mma_16816<FP16>(o[n], pf, b0, b1);
+        mma_16816<FP16>(o[n + 1], pf, b2, b3);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+    // transpose the context block through the (consumed) Q rows of this block: 16-byte row stores
+    __syncwarp();
+    {
+      const int r0 = m0 + g, r1 = m0 + g + 8;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        if (r0 < R)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(q_addr + sw128(r0, 8 * n + 2 * cq)),
+                       "r"(pack16<FP16>(o[n][0] * inv0, o[n][1] * inv0)) : "memory");
+        if (r1 < R)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(q_addr + sw128(r1, 8 * n + 2 * cq)),
+                       "r"(pack16<FP16>(o[n][2] * inv1, o[n][3] * inv1)) : "memory");
+      }
+    }
+    __syncwarp();
+    {
+      const int r_off = lane >> 3, ch = lane & 7;
+#pragma unroll
+      for (int rr = 0; rr < 16; rr += 4) {
+        const int q = m0 + rr + r_off;
+        if (q < T) {
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(q_addr + sw128(q, ch * 8)));
+          *reinterpret_cast<uint4*>(ob + (size_t)q * H + ch * 8) = v;
+        }
+      }
+    }
+  }
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(32 * (1 + ATT_TMA_MAX_HEADS), 1)
+attention_tma_kernel(const __grid_constant__ AttTmaMaps maps, __nv_bfloat16* __restrict__ ctx, CopyPlan plan,
+                     int32_t n_copies, int H, int NH) {
+  extern __shared__ uint8_t att_tma_dyn[];
+  const uint32_t raw = smem_u32(att_tma_dyn);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t stage_bytes = (uint32_t)(3 * NH * ATT_TMA_ROWS * 128);
+  const uint32_t bar_full = base + ATT_TMA_STAGES * stage_bytes;     // ATT_TMA_STAGES x 8 B
+  const uint32_t bar_empty = bar_full + 8 * ATT_TMA_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ATT_TMA_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, (uint32_t)NH);
+    }
+    fence_barrier_init();
+#pragma unroll
+    for (int i = 0; i < ATT_TMA_MAPS; ++i) prefetch_tensormap(&maps.m[i]);
+  }
+  __syncthreads();
+  uint32_t stage = 0, phase = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = blockIdx.x; c < n_copies; c += gridDim.x) {
+        const int T = plan.seq_len[c];
+        if (T > ATT_TMA_ROWS) continue;
+        const int start = plan.seq_start[c];
+        const int R = (T + 7) & ~7;
+        const CUtensorMap* m = &maps.m[(R >> 3) - 1];
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(3 * NH * R * 128));
+        const uint32_t dst = base + stage * stage_bytes;
+        for (int sl = 0; sl < 3 * NH; ++sl)
+          tma_load_2d(dst + (uint32_t)(sl * R * 128), m, bar_full + 8 * stage, sl * 64, start);
+        if (++stage == ATT_TMA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp <= NH) {
+    const int head = warp - 1;
+    for (int c = blockIdx.x; c < n_copies; c += gridDim.x) {
+      const int T = plan.seq_len[c];
+      if (T > ATT_TMA_ROWS) continue;
+      const int start = plan.seq_start[c];
+      const int R = (T + 7) & ~7;
+      mbar_wait(bar_full + 8 * stage, phase);
+      const uint32_t tile = (uint32_t)(R * 128);
+      const uint32_t sb = base + stage * stage_bytes;
+      attn_compute_sw<FP16>(sb + (uint32_t)head * tile, sb + (uint32_t)(NH + head) * tile, sb + (uint32_t)(2 * NH + head) * tile,
+                            ctx + (size_t)start * H + head * 64, T, R, H, lane);
+      fence_proxy_async_smem();      // this warp wrote the tiles (zero fill, output staging) before the next TMA refill
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+      if (++stage == ATT_TMA_STAGES) { stage = 0; phase ^= 1; }
+    }
   }
 }
 
@@ -906,19 +1122,42 @@ int launch_plain_ln_bf16(const float* x, void* out_bf16, const float* g, const f
 }
 
 int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_t n_copies, int H, int NH, int max_T,
-                     bool fp16, bool shared_rows, cudaStream_t s) {
+                     bool fp16, bool shared_rows, int64_t qkv_rows, cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
-  (void)max_T;
+  // TMA-fed persistent kernel for the copies of at most ATT_TMA_ROWS rows (PLLB_ATT_TMA=0 disables)
+  static const bool tma_on = [] { const char* e = getenv("PLLB_ATT_TMA"); return !e || atoi(e) != 0; }();
+  int skip_le = 0;
+  if (tma_on && !shared_rows && NH <= ATT_TMA_MAX_HEADS && qkv_rows > 0) {
+    AttTmaMaps maps;
+    for (int i = 0; i < ATT_TMA_MAPS; ++i) {
+      int rc = get_tmap_2d(&maps.m[i], qkv_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)qkv_rows, (uint64_t)3 * H,
+                           (uint32_t)(8 * (i + 1)), 64);
+      if (rc) return rc;
+    }
+    const int smem = ATT_TMA_STAGES * 3 * NH * ATT_TMA_ROWS * 128 + 16 * ATT_TMA_STAGES + 1024;
+    const int grid = (int)std::min<int64_t>(n_copies, sm_count());
+    const int threads = 32 * (1 + NH);
+    if (fp16) {
+      PLLB_CUDA(opt_in_smem(attention_tma_kernel<true>, smem));
+      attention_tma_kernel<true><<<grid, threads, smem, s>>>(maps, reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H, NH);
+    } else {
+      PLLB_CUDA(opt_in_smem(attention_tma_kernel<false>, smem));
+      attention_tma_kernel<false><<<grid, threads, smem, s>>>(maps, reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H, NH);
+    }
+    PLLB_LAUNCH_CHECK("attention_tma_kernel");
+    skip_le = ATT_TMA_ROWS;
+    if (max_T <= ATT_TMA_ROWS) return PLLB_OK;          // no longer copy in this chunk
+  }
   const int64_t pairs = (int64_t)n_copies * NH;
   const int smem = ATT_WARPS * ATT_STAGE_ELEMS * 2;
   const unsigned grid = (unsigned)ceil_div(pairs, ATT_WARPS);
 #define ATT(F, S)                                                                                                  \
   do {                                                                                                             \
-    PLLB_CUDA(cudaFuncSetAttribute(attention_mma_kernel<F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    PLLB_CUDA(opt_in_smem(attention_mma_kernel<F, S>, smem));                                                      \
     attention_mma_kernel<F, S><<<grid, ATT_WARPS * 32, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_bf16), \
                                                                   reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, \
-                                                                  n_copies, H, NH);                                \
+                                                                  n_copies, H, NH, skip_le);                       \
   } while (0)
   if (fp16) { if (shared_rows) ATT(true, true); else ATT(true, false); }
   else { if (shared_rows) ATT(false, true); else ATT(false, false); }
