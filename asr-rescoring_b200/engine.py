@@ -237,6 +237,36 @@ def pack_strings(strings: Sequence[str]):
     return cp, off
 
 
+_WS = None
+
+
+def _whitespace_code_points() -> np.ndarray:
+    """Code points str.strip() removes (str.isspace()), for the vectorised strip check."""
+    global _WS
+    if _WS is None:
+        _WS = np.array([c for c in range(0x3001) if chr(c).isspace()], np.int32)   # none above U+3000
+    return _WS
+
+
+def pack_stripped(strings: Sequence[str]):
+    """pack_strings([s.strip() for s in strings]) plus the RAW lengths, in one pass over the list:
+    the strings are packed unstripped, and only if some string starts or ends with a whitespace
+    code point (checked on the packed array) is the per-string strip() done.  Returns
+    (code points, offsets, raw lengths int64)."""
+    n = len(strings)
+    raw_len = np.fromiter(map(len, strings), np.int64, n) if n else np.zeros(0, np.int64)
+    off = np.zeros(n + 1, np.int64)
+    np.cumsum(raw_len, out=off[1:])
+    cp = np.frombuffer("".join(strings).encode("utf-32-le", "surrogatepass"), np.int32)
+    assert len(cp) == off[-1]
+    nz = raw_len > 0
+    ws = _whitespace_code_points()
+    if nz.any() and (np.isin(cp[off[:-1][nz]], ws).any() or np.isin(cp[off[1:][nz] - 1], ws).any()):
+        cp, off = pack_strings([s.strip() for s in strings])
+        return cp, off, raw_len
+    return cp.copy(), off, raw_len
+
+
 def tokenize_packed(table: np.ndarray, cp: np.ndarray, cp_off: np.ndarray):
     """pllb_tokenize_host: packed code points -> (ids int32, offsets int64[n+1], needs_host uint8[n])."""
     lib = _lib.load()

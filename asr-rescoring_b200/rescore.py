@@ -76,18 +76,25 @@ def cer(ref, hyp) -> float:
     return float(int(engine.levenshtein(ref, hyp).sum())) / float(total)
 
 
-def pair_distances(hyps, ref, n_best) -> np.ndarray:
-    """int32 [N, n_best] edit distance of every candidate to its reference (one launch)."""
-    refs = [r.strip() for r in ref]
-    flat = [h.strip() for utt in hyps for h in utt[:n_best]]
-    counts = [len(utt[:n_best]) for utt in hyps]
-    if len(set(counts)) > 1:
+def _pack_candidates(hyps, n_best):
+    """First n_best candidates of every utterance, flattened: (code points, offsets) of the stripped
+    strings for the Levenshtein kernel and the RAW lengths [N, n_best] that rescore.py:28-35 uses."""
+    counts = {len(utt[:n_best]) for utt in hyps}
+    if len(counts) > 1:
         raise ValueError("every utterance needs the same number of hypotheses (rectangular N-best), as np.array "
                          "in rescore.py:48-50 requires")
-    rc, ro = engine.pack_strings(refs)
-    hc, ho = engine.pack_strings(flat)
-    pair_ref = np.repeat(np.arange(len(refs), dtype=np.int32), counts[0] if counts else 0)
-    return engine.levenshtein_packed(rc, ro, hc, ho, pair_ref).reshape(len(refs), -1)
+    flat = [h for utt in hyps for h in utt[:n_best]]
+    hc, ho, raw_len = engine.pack_stripped(flat)
+    width = counts.pop() if counts else 0
+    return hc, ho, raw_len.reshape(len(hyps), width), width
+
+
+def pair_distances(hyps, ref, n_best, packed=None) -> np.ndarray:
+    """int32 [N, n_best] edit distance of every candidate to its reference (one launch)."""
+    hc, ho, _, width = packed if packed is not None else _pack_candidates(hyps, n_best)
+    rc, ro = engine.pack_strings([r.strip() for r in ref])
+    pair_ref = np.repeat(np.arange(len(ref), dtype=np.int32), width)
+    return engine.levenshtein_packed(rc, ro, hc, ho, pair_ref).reshape(len(ref), -1)
 
 
 def sweep(am, lm, hyps, ref, config, weights=None):
@@ -107,13 +114,14 @@ def sweep(am, lm, hyps, ref, config, weights=None):
     N = len(ref)
     lo, hi = shard.block_range(N, rank, world)
     hyps_l, ref_l = hyps[lo:hi], ref[lo:hi]
-    hyps_len = np.array(_hyps_len(hyps_l, n_best), np.int64).reshape(hi - lo, -1)
+    packed = _pack_candidates(hyps_l, n_best)          # one pass over the strings: lengths + code points
+    hyps_len = packed[2]
     am_ = np.array(am[lo:hi], np.float64).reshape(hi - lo, -1)[:, :n_best]
     lm_ = np.array(lm[lo:hi], np.float64).reshape(hi - lo, -1)
     counts = np.zeros(len(weights) + 1, np.int64)
     argmax = np.zeros((len(weights), hi - lo), np.int32)
     if hi > lo:
-        dist = pair_distances(hyps_l, ref_l, n_best)
+        dist = pair_distances(hyps_l, ref_l, n_best, packed)
         argmax, edits = engine.rescore_sweep(am_, lm_, hyps_len, dist, weights, _formula(config))
         counts[:-1] = edits
         counts[-1] = sum(len(r.strip()) for r in ref_l)

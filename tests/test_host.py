@@ -329,3 +329,14 @@ def test_bench_reference_arm_combiner_workload():
     assert out.returncode == 0, out.stderr[-1500:]
     d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
     assert d["impl"] == "reference" and d["value"] > 0 and 0.0 <= d["best_weight"] <= 1.0 and d["dtype"] == "f64"
+
+
+def test_pack_stripped_equals_strip_then_pack():
+    """The combiner's one-pass packing (raw lengths for rescore.py:28-35, stripped code points for the
+    CER) against the plain per-string strip(), incl. every whitespace code point str.strip() knows."""
+    from asr_rescoring_b200 import engine
+    for strs in (["你好", " a b ", "", "　x　", "xyz\n", "\x85q", " "], ["abc", "", "好"], []):
+        cp, off, raw = engine.pack_stripped(strs)
+        cp2, off2 = engine.pack_strings([s.strip() for s in strs])
+        assert np.array_equal(cp, cp2) and np.array_equal(off, off2) and list(raw) == [len(s) for s in strs]
+    assert sorted(c for c in range(0x110000) if chr(c).isspace()) == sorted(engine._whitespace_code_points().tolist())
