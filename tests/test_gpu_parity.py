@@ -722,3 +722,20 @@ def test_fp16_conversions_saturate_instead_of_overflowing():
         with engine.PllScorer(sd, cfg, operand_dtype=mode) as sc:
             got = sc.score_packed(tok, off)
         assert np.isfinite(got).all() and np.abs(got - exp).max() <= tol, (mode, np.abs(got - exp).max())
+
+
+def test_two_gpu_drop_in_outputs_identical_to_one_gpu():
+    """N GPUs == 1 GPU, bitwise: MLM_PLL/main.py on text and on row-list inputs (num_of_data cutting a
+    hypothesis), and rescore.py with the sharded sweep + all_reduce of the CER counts
+    (tools/e2e_dropin.py --gpus 2).  Needs two visible B200s; the single-GPU test box skips it, the
+    builder's 2-GPU run is kept as profiles/r02_identity_2gpu.log."""
+    import subprocess
+    import sys
+    from asr_rescoring_b200 import _lib
+    if _lib.load().pllb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "e2e_dropin.py"), "--gpus", "2"],
+                         capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert "identical to the 1-GPU files" in out.stdout and "row-list input" in out.stdout and "sharded sweep" in out.stdout

@@ -340,3 +340,28 @@ def test_pack_stripped_equals_strip_then_pack():
         cp2, off2 = engine.pack_strings([s.strip() for s in strs])
         assert np.array_equal(cp, cp2) and np.array_equal(off, off2) and list(raw) == [len(s) for s in strs]
     assert sorted(c for c in range(0x110000) if chr(c).isspace()) == sorted(engine._whitespace_code_points().tolist())
+
+
+def test_preprocess_main_writes_the_three_packed_splits(tmp_path):
+    """MLM_PLL/preprocess.py __main__ (reference: preprocess.py:33-72): the three for_scoring jobs, run
+    from an MLM_PLL working directory with the relative paths of the reference."""
+    tk = SyntheticCharTokenizer()
+    (tmp_path / "MLM_PLL").mkdir()
+    texts = {}
+    for split in ("train", "dev", "test"):
+        d = tmp_path / "espnet_data" / "alfred" / split
+        d.mkdir(parents=True)
+        texts[split] = {f"{split}_u{i}": {"hyp_1": "你好嗎", "hyp_2": "", "hyp_3": "好"} for i in range(3)}
+        (d / "hyps_text.json").write_text(json.dumps(texts[split], ensure_ascii=False), encoding="utf-8")
+    script = os.path.join(ROOT, "asr-rescoring_b200", "MLM_PLL", "preprocess.py")
+    env = {k: v for k, v in os.environ.items() if k != "PLLB_VOCAB"}
+    out = subprocess.run([sys.executable, script], cwd=tmp_path / "MLM_PLL", env=env, capture_output=True, text=True)
+    assert out.returncode != 0 and "PLLB_VOCAB" in (out.stderr + out.stdout)        # no silent synthetic tokenizer
+    out = subprocess.run([sys.executable, script], cwd=tmp_path / "MLM_PLL", env=dict(env, PLLB_SYNTHETIC_TOKENIZER="1"),
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-1500:]
+    for split in ("train", "dev", "test"):
+        p = json.load(open(tmp_path / "MLM_PLL" / "preprocessed_data" / "for_scoring" / f"{split}.json", encoding="utf-8"))
+        assert p["format"] == "pllb-packed-v1" and p["tokenizer"] == "synthetic"
+        assert p["utt_id"] == [u for u in texts[split] for _ in range(3)] and p["hyp_id"] == ["hyp_1", "hyp_2", "hyp_3"] * 3
+        assert p["offsets"] == [0, 3, 3, 4, 7, 7, 8, 11, 11, 12] and p["tokens"][:3] == tk.encode("你好嗎")
