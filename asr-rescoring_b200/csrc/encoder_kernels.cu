@@ -601,9 +601,12 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 // ---------------------------------------------------------------- TMA-fed varlen attention
 // Persistent form for the layers whose Q|K|V rows are the copy's own packed rows (every layer but
-// the shared layer 0 and the pruned last one).  attention_mma_kernel above stages one (copy, head)
-// per warp and then computes: a warp has no load in flight while it computes, so the kernel is
-// latency-bound (0.67 of the HBM peak).  Here one CTA walks over whole masked copies:
+// the shared layer 0 and the pruned last one), written to test the hypothesis that
+// attention_mma_kernel (one (copy, head) staged per warp, no load in flight while the warp
+// computes) is latency-bound at its 0.67 of the HBM peak.  It is not: this kernel keeps ~100 KB per
+// SM in flight and reaches the same rate, because both spend ~900 warp instructions per (copy,
+// head) and are bound by instruction issue.  Kept as an opt-in (PLLB_ATT_TMA=1), bit-identical to
+// the default kernel.  One CTA walks over whole masked copies:
 //   warp 0        producer — per copy 3*NH TMA box loads (Q, K, V slice of every head: 64 columns x
 //                 R rows, R = T rounded up to 8, 128-byte swizzle) into a 2-stage ring, one mbarrier
 //                 transaction per stage; the next copy streams in while this one is computed, so
@@ -1125,8 +1128,12 @@ int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_
                      bool fp16, bool shared_rows, int64_t qkv_rows, cudaStream_t s) {
   if (n_copies <= 0) return PLLB_OK;
   if (H != NH * 64) return fail(PLLB_ERR_INVALID, "attention: head dim must be 64");
-  // TMA-fed persistent kernel for the copies of at most ATT_TMA_ROWS rows (PLLB_ATT_TMA=0 disables)
-  static const bool tma_on = [] { const char* e = getenv("PLLB_ATT_TMA"); return !e || atoi(e) != 0; }();
+  // TMA-fed persistent kernel for the copies of at most ATT_TMA_ROWS rows: opt-in (PLLB_ATT_TMA=1).
+  // Measured (round 2, ncu): it moves the same bytes no faster than attention_mma_kernel — both are
+  // bound by instruction issue (~900 warp instructions per (copy, head), issue slots 50 % busy with
+  // the 13-16 warps per SM that 128 registers allow), not by load latency — see DESIGN.md §3.2.
+  const char* tma_env = getenv("PLLB_ATT_TMA");
+  const bool tma_on = tma_env && atoi(tma_env) != 0;
   int skip_le = 0;
   if (tma_on && !shared_rows && NH <= ATT_TMA_MAX_HEADS && qkv_rows > 0) {
     AttTmaMaps maps;
@@ -1136,13 +1143,14 @@ int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_
       if (rc) return rc;
     }
     const int smem = ATT_TMA_STAGES * 3 * NH * ATT_TMA_ROWS * 128 + 16 * ATT_TMA_STAGES + 1024;
+    const int smem_max = ATT_TMA_STAGES * 3 * ATT_TMA_MAX_HEADS * ATT_TMA_ROWS * 128 + 16 * ATT_TMA_STAGES + 1024;
     const int grid = (int)std::min<int64_t>(n_copies, sm_count());
     const int threads = 32 * (1 + NH);
     if (fp16) {
-      PLLB_CUDA(opt_in_smem(attention_tma_kernel<true>, smem));
+      PLLB_CUDA(opt_in_smem(attention_tma_kernel<true>, smem_max));
       attention_tma_kernel<true><<<grid, threads, smem, s>>>(maps, reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H, NH);
     } else {
-      PLLB_CUDA(opt_in_smem(attention_tma_kernel<false>, smem));
+      PLLB_CUDA(opt_in_smem(attention_tma_kernel<false>, smem_max));
       attention_tma_kernel<false><<<grid, threads, smem, s>>>(maps, reinterpret_cast<__nv_bfloat16*>(ctx_bf16), plan, n_copies, H, NH);
     }
     PLLB_LAUNCH_CHECK("attention_tma_kernel");
