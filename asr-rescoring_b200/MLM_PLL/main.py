@@ -270,6 +270,10 @@ def pll_bert_scoring(config):
         if rank == 0:
             json_saving(config.output_path + f"{split}_lm.json", output_score)   # string concat as main.py:203
     model.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def mlm_finetune_bert(config):
