@@ -654,7 +654,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
 
   // workspace: sized by the expanded-token budget of one chunk
   if (max_chunk_tokens <= 0) max_chunk_tokens = (int64_t)1 << 20;
-  c->cap_rows = align_up(std::max<int64_t>(max_chunk_tokens, 1024), 128);
+  c->cap_rows = align_up(std::max<int64_t>(max_chunk_tokens, 1024), 256);   // the paired LayerNorm clusters work on 256-row blocks
   c->cap_copies = c->cap_rows / 4 + 128;
   c->cap_hyps = c->cap_rows / 4 + 128;
   const int64_t R = c->cap_rows, C = c->cap_copies;
@@ -673,7 +673,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   TRY(dev_alloc(c, &c->plan.row_src, R));
   TRY(dev_alloc(c, &c->hg, C * H));
   TRY(dev_alloc(c, &c->t_f32, C * H));
-  TRY(dev_alloc(c, &c->hid_c, align_up(C, 128) * H));
+  TRY(dev_alloc(c, &c->hid_c, align_up(C, 256) * H));
   TRY(dev_alloc(c, &c->t_bf16, C * H));
   TRY(dev_alloc(c, &c->partials, C * c->tiles_v * 2));
   TRY(dev_alloc(c, &c->label_logit, C));

@@ -50,13 +50,18 @@ constexpr int MAX_CN = 4;
 
 constexpr int SMEM_XCHG = 2 * 2 * MAX_CN * BM * 8;                         // [parity][rank*2+half][row] float2
 constexpr int SMEM_BARS = 512;
-template <bool STAGED>
+template <bool STAGED, bool PAIR>
+constexpr int ln_stages() {
+  return PAIR ? (STAGED ? 4 : 6) : (STAGED ? 3 : 4);
+}
+template <bool STAGED, bool PAIR>
 constexpr int smem_total() {
-  return (STAGED ? 3 : 4) * (A_STAGE_BYTES + B_STAGE_BYTES) + (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + SMEM_XCHG + SMEM_BARS +
-         1024;
+  return ln_stages<STAGED, PAIR>() * (A_STAGE_BYTES + (PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES)) +
+         (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + SMEM_XCHG + SMEM_BARS + 1024;
 }
 
-static_assert(smem_total<true>() <= 232448 && smem_total<false>() <= 232448, "shared memory budget of one CTA");
+static_assert(smem_total<true, false>() <= 232448 && smem_total<false, false>() <= 232448 &&
+              smem_total<true, true>() <= 232448 && smem_total<false, true>() <= 232448, "shared memory budget of one CTA");
 
 struct LnParams {
   int M, K, H;
@@ -120,13 +125,22 @@ __device__ __forceinline__ float4 ldg_f4_ordered(const float* p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-template <int CN, int DT, bool STAGED>
+// PAIR: the cluster holds 2*CN CTAs and covers a 256-row block.  CTAs 2c and 2c+1 form a
+// cta_group::2 pair on column group c: the leader issues ONE tcgen05.mma with M = 256 per k-step,
+// each CTA stages its own 128 rows of A and only HALF of the 256 x 64 W box (a stage is 32 KiB
+// instead of 48, the ring 6 / 4 deep instead of 4 / 3).  A single-CTA 128x256x16 MMA reads 12 KB
+// of operands from shared memory per 128 tensor cycles while TMA writes the next stage — the
+// shared-memory port, not the tensor pipe, paces that form (tensor pipe 63-67 % active in ncu);
+// the pair reads 8 KB per CTA.  LayerNorm statistics are exchanged between the CN CTAs that hold
+// the same rows (ranks rh, 2 + rh, 4 + rh).
+template <int CN, int DT, bool STAGED, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmH16, const LnParams p) {
   constexpr bool FP16 = (DT & 4) != 0;          // type of the 16-bit output copy
-  constexpr int STAGES = STAGED ? 3 : 4;
-  constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  constexpr int STAGES = ln_stages<STAGED, PAIR>();
+  constexpr int B_BYTES = PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
+  constexpr int SMEM_PIPE = STAGES * (A_STAGE_BYTES + B_BYTES);
   constexpr int SMEM_EPI = STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -149,17 +163,22 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = CN > 1 ? cluster_ctarank() : 0;
-  const int cluster = CN > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int n_clusters = CN > 1 ? (int)num_clusters_x() : (int)gridDim.x;
-  const int tiles_m = (p.M + BM - 1) / BM;
+  constexpr bool CLUSTERED = CN > 1 || PAIR;
+  const uint32_t rank = CLUSTERED ? cluster_ctarank() : 0;
+  const uint32_t cg = PAIR ? rank >> 1 : rank;             // column group: columns [256 cg, 256 cg + 256)
+  const uint32_t rh = PAIR ? rank & 1u : 0u;               // row half inside the 256-row block; 0 = leader of the pair
+  const uint32_t leader = rank & ~1u;
+  constexpr int ROWS = PAIR ? 2 * BM : BM;                 // rows of a block per cluster
+  const int cluster = CLUSTERED ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int n_clusters = CLUSTERED ? (int)num_clusters_x() : (int)gridDim.x;
+  const int tiles_m = (p.M + ROWS - 1) / ROWS;
   const int num_kb = p.K / BK;
-  const int n0 = (int)rank * BN;
+  const int n0 = (int)cg * BN;
   // All CN CTAs of a cluster multiply the SAME 128 x K block of A by their own 256 columns of W.
   // With amc the A stage (four 32-row boxes) is fetched from L2 once per cluster: CTA r issues
   // boxes r, r+CN, ... as TMA multicasts into every CTA's stage, and a stage is reused only after
   // every CTA's MMAs released it (their commits are multicast to all empty barriers).
-  const bool amc = CN > 1 && p.amc != 0;
+  const bool amc = !PAIR && CN > 1 && p.amc != 0;
   constexpr uint16_t mask_all = (uint16_t)((1u << CN) - 1u);
   constexpr int A_BOX_ROWS = 32, A_BOX_BYTES = A_BOX_ROWS * BK * 2;
 
@@ -175,18 +194,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
-        mbar_init(bar_tempty + 8 * s, EPI_WARPS);
+        mbar_init(bar_tempty + 8 * s, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // PAIR: both CTAs' epilogues report to the leader
         mbar_init(bar_x + 8 * s, 1);                       // armed once per tile with the expected byte count
       }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (CN > 1) cluster_sync_all();          // peers' barriers are initialised before any remote arrive
+  if (CLUSTERED) cluster_sync_all();       // peers' barriers are initialised before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -194,9 +218,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
-        const int m0 = mb * BM;
+        const int m0 = mb * ROWS + (int)rh * BM;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if constexpr (PAIR) {
+            // both CTAs' bytes are counted on the leader's barrier, which only the leader arms
+            const uint32_t lead_full = mapa_shared(bar_full + 8 * stage, leader);
+            if (rh == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (A_STAGE_BYTES + B_BYTES));
+#pragma unroll
+            for (int b = 0; b < BM / A_BOX_ROWS; ++b)
+              tma_load_2d_2sm(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, lead_full, kb * BK, m0 + b * A_BOX_ROWS);
+            tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, n0 + (int)rh * (BN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
           tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
           if (amc) {
@@ -214,8 +249,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_16(BM, BN, (DT & 1) != 0, (DT & 2) != 0);
+    if (lane == 0 && (!PAIR || rh == 0)) {                    // PAIR: the leader issues for both CTAs
+      constexpr uint32_t idesc = make_idesc_16(PAIR ? 2 * BM : BM, BN, (DT & 1) != 0, (DT & 2) != 0);
+      const uint16_t mask_pair = (uint16_t)(0x3u << leader);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -225,17 +261,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(bar_full + 8 * stage, phase);
           tcgen05_fence_after();
           const uint32_t a_addr = sA + stage * A_STAGE_BYTES;
-          const uint32_t b_addr = sB + stage * B_STAGE_BYTES;
+          const uint32_t b_addr = sB + stage * B_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            tcgen05_mma_bf16(d_tmem, make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2),
-                             make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR)
+              tcgen05_mma_bf16_2cta(d_tmem, make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2),
+                                    make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              tcgen05_mma_bf16(d_tmem, make_kmajor_sw128_desc(a_addr + k * UMMA_K * 2),
+                               make_kmajor_sw128_desc(b_addr + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (amc) tcgen05_commit_multicast(bar_empty + 8 * stage, mask_all);
+          if constexpr (PAIR) tcgen05_commit_2cta_multicast(bar_empty + 8 * stage, mask_pair);
+          else if (amc) tcgen05_commit_multicast(bar_empty + 8 * stage, mask_all);
           else tcgen05_commit(bar_empty + 8 * stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(bar_tfull + 8 * acc);
+        if constexpr (PAIR) tcgen05_commit_2cta_multicast(bar_tfull + 8 * acc, mask_pair);
+        else tcgen05_commit(bar_tfull + 8 * acc);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -269,7 +311,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NCH = EPI_COLS / 16;         // 8 chunks of 16 columns
 
     for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
-      const int m0 = mb * BM;
+      const int m0 = mb * ROWS + (int)rh * BM;
       const int grow0 = m0 + q * 32;                         // first global row of this warp
       float4* hrow = reinterpret_cast<float4*>(p.hidden) + ((size_t)(grow0 >> 5) * groups_per_row + g0) * 32 + lane;
 
@@ -319,12 +361,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       // ---- exchange (mean, M2) of the 2*CN column groups of every row
       {
-        const uint32_t slot = sXchg + (uint32_t)((xpar * (2 * MAX_CN) + rank * 2 + half) * BM + row_in_tile) * 8;
+        const uint32_t slot = sXchg + (uint32_t)((xpar * (2 * MAX_CN) + cg * 2 + half) * BM + row_in_tile) * 8;
         const uint32_t xb = bar_x + 8 * xpar;
         if (ew == 0 && lane == 0) mbar_arrive_expect_tx(xb, CN * EPI_WARPS * 32 * 8);   // this tile's inbox
 #pragma unroll
-        for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer)
-          st_async_f32x2(mapa(slot, peer), mean_t, m2_t, mapa(xb, peer));
+        for (uint32_t peer = 0; peer < (uint32_t)CN; ++peer) {
+          const uint32_t pr = PAIR ? 2 * peer + rh : peer;    // the CTA that holds the same rows of column group `peer`
+          st_async_f32x2(mapa(slot, pr), mean_t, m2_t, mapa(xb, pr));
+        }
         const uint32_t ph = xpar ? xphase1 : xphase0;
         mbar_wait(xb, ph);
         if (xpar) xphase1 ^= 1; else xphase0 ^= 1;
@@ -392,7 +436,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // accumulator columns are free again
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, leader));   // the leader's MMA waits for both CTAs
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if constexpr (STAGED) {
@@ -412,11 +459,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tcgen05_fence_before();
   __syncthreads();
-  if (CN > 1) cluster_sync_all();          // no CTA leaves while a peer may still address its shared memory
+  if (CLUSTERED) cluster_sync_all();       // no CTA leaves while a peer may still address its shared memory
   if (warp == 1) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -425,11 +473,12 @@ int tmap2d(CUtensorMap* m, const void* base, CUtensorMapDataType dt, int elt, ui
   return get_tmap_2d(m, base, dt, elt, rows, cols, box_rows, box_cols);
 }
 
-template <int CN, int DT, bool STAGED>
+template <int CN, int DT, bool STAGED, bool PAIR>
 int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t16,
-              const LnParams& lp, int64_t tiles_m, cudaStream_t stream) {
-  auto kern = gemm_ln_kernel<CN, DT, STAGED>;
-  constexpr int SMEM_TOTAL = smem_total<STAGED>();
+              const LnParams& lp, int64_t M, cudaStream_t stream) {
+  auto kern = gemm_ln_kernel<CN, DT, STAGED, PAIR>;
+  constexpr int SMEM_TOTAL = smem_total<STAGED, PAIR>();
+  constexpr int CSIZE = PAIR ? 2 * CN : CN;
   PLLB_CUDA(opt_in_smem(kern, SMEM_TOTAL));
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(NUM_THREADS);
@@ -437,32 +486,42 @@ int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CN;
+  attr[0].val.clusterDim.x = CSIZE;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent: as many clusters as can be co-resident (clusters must fit inside a GPC)
-  static thread_local int max_clusters[MAX_CN + 1][16] = {};
-  int& mc = max_clusters[CN][DT + (STAGED ? 8 : 0)];
+  static thread_local int max_clusters[MAX_CN + 1][32] = {};
+  int& mc = max_clusters[CN][DT + (STAGED ? 8 : 0) + (PAIR ? 16 : 0)];
   if (mc == 0) {
-    cfg.gridDim = dim3(CN * (sm_count() / CN));
+    cfg.gridDim = dim3(CSIZE * (sm_count() / CSIZE));
     int n = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
     if (e != cudaSuccess || n <= 0) {
       cudaGetLastError();
-      n = sm_count() / CN;
+      n = sm_count() / CSIZE;
     }
     mc = n;
   }
   // PLLB_LN_MAX_CLUSTERS: experiment knob (how does the step react to fewer SMs under the power cap?)
   static const int cap = [] { const char* e = getenv("PLLB_LN_MAX_CLUSTERS"); return e ? atoi(e) : 0; }();
   const int limit = cap > 0 && cap < mc ? cap : mc;
+  const int64_t tiles_m = ceil_div(M, PAIR ? 2 * BM : BM);
   const int clusters = (int)(tiles_m < limit ? tiles_m : limit);
-  cfg.gridDim = dim3(CN * clusters);
+  cfg.gridDim = dim3(CSIZE * clusters);
   PLLB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t16, lp));
   ++g_launch_counter;
   return PLLB_OK;
+}
+
+template <int CN, int DT>
+int launch_cn_dt(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t16, const LnParams& lp, int64_t M,
+                 bool staged, bool pair, cudaStream_t stream) {
+  if (pair) return staged ? launch_cn<CN, DT, true, true>(ta, tb, t16, lp, M, stream)
+                          : launch_cn<CN, DT, false, true>(ta, tb, t16, lp, M, stream);
+  return staged ? launch_cn<CN, DT, true, false>(ta, tb, t16, lp, M, stream)
+                : launch_cn<CN, DT, false, false>(ta, tb, t16, lp, M, stream);
 }
 
 }  // namespace
@@ -472,34 +531,37 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   if (M <= 0) return PLLB_OK;
   if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
+  // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
+  const bool staged = K <= H;
+  // cta_group::2 pairs inside the LayerNorm cluster (PLLB_LN_PAIR: 0 never, 1 default policy, 2 always).
+  // Default: the mainloop-paced launches (K > H, i.e. FFN2) of the shapes whose doubled cluster still
+  // covers the chip — H = 256 (cluster 2: 148 SMs) and H = 768 (cluster 6: 132 of 148 SMs vs 135);
+  // H = 512 / 1024 would drop from 148 / 132 to 132 / 120 SMs.
+  const char* pe = getenv("PLLB_LN_PAIR");
+  const int pair_policy = pe ? atoi(pe) : 1;
+  const int cn = H / BN;
+  const bool pair = M > 2 * BM && (pair_policy >= 2 || (pair_policy == 1 && !staged && (cn == 1 || cn == 3)));
   CUtensorMap ta, tb, t16;
   int rc;
   if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
-  if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, BN, BK))) return rc;
+  if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, pair ? BN / 2 : BN, BK))) return rc;
   if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
   static const int amc = [] { const char* e = getenv("PLLB_LN_AMC"); return e ? atoi(e) : 1; }();
   LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps, amc};
-  const int64_t tiles_m = ceil_div(M, BM);
-  // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
-  const bool staged = K <= H;
-#define PLLB_LN_DT(CN_, DT_)                                                                                  \
-  return staged ? launch_cn<CN_, DT_, true>(ta, tb, t16, lp, tiles_m, stream)                                 \
-                : launch_cn<CN_, DT_, false>(ta, tb, t16, lp, tiles_m, stream);
 #define PLLB_LN(CN_)                                                                                          \
   case CN_:                                                                                                   \
     switch (dt) {                                                                                             \
-      case DT_BF16: PLLB_LN_DT(CN_, DT_BF16)                                                                  \
-      case DT_BF16_OUT16: PLLB_LN_DT(CN_, DT_BF16_OUT16)                                                      \
-      case DT_FP16: PLLB_LN_DT(CN_, DT_FP16)                                                                  \
+      case DT_BF16: return launch_cn_dt<CN_, DT_BF16>(ta, tb, t16, lp, M, staged, pair, stream);              \
+      case DT_BF16_OUT16: return launch_cn_dt<CN_, DT_BF16_OUT16>(ta, tb, t16, lp, M, staged, pair, stream);  \
+      case DT_FP16: return launch_cn_dt<CN_, DT_FP16>(ta, tb, t16, lp, M, staged, pair, stream);              \
     }                                                                                                         \
     return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported operand dtype combination");
-  switch (H / BN) {
+  switch (cn) {
     PLLB_LN(1)
     PLLB_LN(2)
     PLLB_LN(3)
     PLLB_LN(4)
   }
-#undef PLLB_LN_DT
 #undef PLLB_LN
   return fail(PLLB_ERR_INVALID, "gemm_ln: unsupported hidden size");
 }

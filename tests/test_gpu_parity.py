@@ -763,3 +763,33 @@ def test_tma_fed_attention_kernel_is_bit_identical(monkeypatch):
             b, tb = sc.score_packed(tok, off, return_token_logp=True)
         monkeypatch.delenv("PLLB_ATT_TMA", raising=False)
         assert np.array_equal(a, b) and np.array_equal(ta, tb) and np.isfinite(a).all(), hidden
+
+
+def test_paired_layernorm_clusters_match_the_single_cta_form(monkeypatch):
+    """gemm_ln_kernel<.., PAIR>: cta_group::2 pairs inside the LayerNorm cluster (256-row blocks, M = 256
+    MMAs, half of the W box per CTA) against the single-CTA form (PLLB_LN_PAIR=0) and the forced form
+    for every launch (PLLB_LN_PAIR=2), for all four cluster sizes and row counts around the 256-row
+    block size; and both against the fp32 oracle."""
+    rng = np.random.default_rng(7)
+    for hidden in (256, 512, 768, 1024):
+        cfg = dict(num_layers=3, hidden=hidden, num_heads=hidden // 64, intermediate=4 * hidden, vocab=1300,
+                   max_position=64, type_vocab=2, ln_eps=1e-12)
+        sd = synth.random_init_state_dict(cfg, 23, perturb=True)
+        lens = [int(x) for x in rng.integers(1, 30, size=50)]
+        off = np.zeros(len(lens) + 1, np.int64)
+        np.cumsum(lens, out=off[1:])
+        tok = rng.integers(104, cfg["vocab"], size=int(off[-1])).astype(np.int32)
+        got = {}
+        for policy in ("0", "1", "2"):
+            monkeypatch.setenv("PLLB_LN_PAIR", policy)
+            with engine.PllScorer(sd, cfg, max_chunk_tokens=8192) as sc:
+                got[policy] = sc.score_packed(tok, off)
+        monkeypatch.delenv("PLLB_LN_PAIR", raising=False)
+        d1, d2 = np.abs(got["1"] - got["0"]).max(), np.abs(got["2"] - got["0"]).max()
+        print(f"H={hidden}: paired vs single-CTA LayerNorm clusters: max |dPLL| default policy {d1:.2e}, forced {d2:.2e}")
+        assert d1 <= 2e-3 and d2 <= 2e-3, (hidden, d1, d2)
+        hyps = {"u": {f"hyp_{i + 1}": [int(t) for t in tok[off[i]:off[i + 1]]] for i in range(10)}}
+        ref = pll_oracle.score_hyps(sd, cfg, hyps)
+        for policy in ("0", "2"):
+            for i in range(10):
+                assert abs(got[policy][i] - ref["u"][f"hyp_{i + 1}"]) <= PLL_TOL, (hidden, policy, i)
