@@ -533,14 +533,16 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
   // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
   const bool staged = K <= H;
-  // cta_group::2 pairs inside the LayerNorm cluster (PLLB_LN_PAIR: 0 never, 1 default policy, 2 always).
+  // cta_group::2 pairs inside the LayerNorm cluster (PLLB_LN_PAIR: 0 never, 1 default policy, 2 always,
+  // 3 every mainloop-paced launch whatever the hidden size).
   // Default: the mainloop-paced launches (K > H, i.e. FFN2) of the shapes whose doubled cluster still
   // covers the chip — H = 256 (cluster 2: 148 SMs) and H = 768 (cluster 6: 132 of 148 SMs vs 135);
   // H = 512 / 1024 would drop from 148 / 132 to 132 / 120 SMs.
   const char* pe = getenv("PLLB_LN_PAIR");
   const int pair_policy = pe ? atoi(pe) : 1;
   const int cn = H / BN;
-  const bool pair = M > 2 * BM && (pair_policy >= 2 || (pair_policy == 1 && !staged && (cn == 1 || cn == 3)));
+  const bool pair = M > 2 * BM && (pair_policy == 2 || (pair_policy == 3 && !staged) ||
+                                   (pair_policy == 1 && !staged && (cn == 1 || cn == 3)));
   CUtensorMap ta, tb, t16;
   int rc;
   if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
