@@ -286,6 +286,14 @@ ln_kernel(const float* __restrict__ y, float* __restrict__ hidden_f32, __nv_bflo
 constexpr int ATT_WARPS = 8;
 constexpr int ATT_VROW = 72;   // bf16 elements per staged V row (144 B: conflict-free ldmatrix)
 
+// 2^x on the SFU alone (MUFU.EX2; exp2f() wraps it in a range check and two scalings that the
+// softmax does not need: its arguments are <= 0 and an underflow to 0 is the right answer).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <bool FP16>
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   if constexpr (FP16) {
@@ -353,6 +361,7 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ ba
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        if (j == 1 && k0 + 8 >= T) break;               // second key tile fully masked (warp-uniform)
         const int key = min(k0 + 8 * j + g, T - 1);
         const __nv_bfloat16* kr = kb + rm(key) + 2 * cq;
 #pragma unroll
@@ -379,16 +388,16 @@ __device__ __forceinline__ void attn_stream(const __nv_bfloat16* __restrict__ ba
         bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
         bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
         const float nm = fmaxf(mx[r], bm[r]);       // finite: every key block holds >= 1 valid key
-        corr[r] = exp2f(mx[r] - nm);
+        corr[r] = fast_ex2(mx[r] - nm);
         mx[r] = nm;
         l[r] *= corr[r];
       }
       uint32_t pf[4];
       {
-        const float p00 = exp2f(s[0][0] - mx[0]), p01 = exp2f(s[0][1] - mx[0]);
-        const float p02 = exp2f(s[0][2] - mx[1]), p03 = exp2f(s[0][3] - mx[1]);
-        const float p10 = exp2f(s[1][0] - mx[0]), p11 = exp2f(s[1][1] - mx[0]);
-        const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
+        const float p00 = fast_ex2(s[0][0] - mx[0]), p01 = fast_ex2(s[0][1] - mx[0]);
+        const float p02 = fast_ex2(s[0][2] - mx[1]), p03 = fast_ex2(s[0][3] - mx[1]);
+        const float p10 = fast_ex2(s[1][0] - mx[0]), p11 = fast_ex2(s[1][1] - mx[0]);
+        const float p12 = fast_ex2(s[1][2] - mx[1]), p13 = fast_ex2(s[1][3] - mx[1]);
         l[0] += (p00 + p01) + (p10 + p11);
         l[1] += (p02 + p03) + (p12 + p13);
         pf[0] = pack16<FP16>(p00, p01); pf[1] = pack16<FP16>(p02, p03);
@@ -482,6 +491,7 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ ba
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        if (j == 1 && k0 + 8 >= T) break;               // second key tile fully masked (warp-uniform)
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {                 // two k-steps per ldmatrix.x4
           const uint32_t addr = k_addr + (uint32_t)((k0 + 8 * j + (lane & 7)) * ATT_VROW + 32 * kp + (lane >> 3) * 8) * 2;
@@ -509,16 +519,16 @@ __device__ __forceinline__ void attn_staged(const __nv_bfloat16* __restrict__ ba
         bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
         bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
         const float nm = fmaxf(mx[r], bm[r]);
-        corr[r] = exp2f(mx[r] - nm);
+        corr[r] = fast_ex2(mx[r] - nm);
         mx[r] = nm;
         l[r] *= corr[r];
       }
       uint32_t pf[4];
       {
-        const float p00 = exp2f(s[0][0] - mx[0]), p01 = exp2f(s[0][1] - mx[0]);
-        const float p02 = exp2f(s[0][2] - mx[1]), p03 = exp2f(s[0][3] - mx[1]);
-        const float p10 = exp2f(s[1][0] - mx[0]), p11 = exp2f(s[1][1] - mx[0]);
-        const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
+        const float p00 = fast_ex2(s[0][0] - mx[0]), p01 = fast_ex2(s[0][1] - mx[0]);
+        const float p02 = fast_ex2(s[0][2] - mx[1]), p03 = fast_ex2(s[0][3] - mx[1]);
+        const float p10 = fast_ex2(s[1][0] - mx[0]), p11 = fast_ex2(s[1][1] - mx[0]);
+        const float p12 = fast_ex2(s[1][2] - mx[1]), p13 = fast_ex2(s[1][3] - mx[1]);
         l[0] += (p00 + p01) + (p10 + p11);
         l[1] += (p02 + p03) + (p12 + p13);
         pf[0] = pack16<FP16>(p00, p01); pf[1] = pack16<FP16>(p02, p03);
@@ -662,6 +672,7 @@ __device__ __forceinline__ void attn_compute_sw(uint32_t q_addr, uint32_t k_addr
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        if (j == 1 && k0 + 8 >= T) break;               // second key tile fully masked (warp-uniform)
         const int krow = min(k0 + 8 * j + (lane & 7), rmax);
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
@@ -689,16 +700,16 @@ __device__ __forceinline__ void attn_compute_sw(uint32_t q_addr, uint32_t k_addr
         bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 1));
         bm[r] = fmaxf(bm[r], __shfl_xor_sync(0xffffffffu, bm[r], 2));
         const float nm = fmaxf(mx[r], bm[r]);
-        corr[r] = exp2f(mx[r] - nm);
+        corr[r] = fast_ex2(mx[r] - nm);
         mx[r] = nm;
         l[r] *= corr[r];
       }
       uint32_t pf[4];
       {
-        const float p00 = exp2f(s[0][0] - mx[0]), p01 = exp2f(s[0][1] - mx[0]);
-        const float p02 = exp2f(s[0][2] - mx[1]), p03 = exp2f(s[0][3] - mx[1]);
-        const float p10 = exp2f(s[1][0] - mx[0]), p11 = exp2f(s[1][1] - mx[0]);
-        const float p12 = exp2f(s[1][2] - mx[1]), p13 = exp2f(s[1][3] - mx[1]);
+        const float p00 = fast_ex2(s[0][0] - mx[0]), p01 = fast_ex2(s[0][1] - mx[0]);
+        const float p02 = fast_ex2(s[0][2] - mx[1]), p03 = fast_ex2(s[0][3] - mx[1]);
+        const float p10 = fast_ex2(s[1][0] - mx[0]), p11 = fast_ex2(s[1][1] - mx[0]);
+        const float p12 = fast_ex2(s[1][2] - mx[1]), p13 = fast_ex2(s[1][3] - mx[1]);
         l[0] += (p00 + p01) + (p10 + p11);
         l[1] += (p02 + p03) + (p12 + p13);
         pf[0] = pack16<FP16>(p00, p01); pf[1] = pack16<FP16>(p02, p03);
@@ -874,7 +885,7 @@ attention_row_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* _
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float sum = 0.f;
   for (int j = r_off; j < T; j += 4) {
-    const float pj = exp2f(ps[w][j] - mx);
+    const float pj = fast_ex2(ps[w][j] - mx);
     sum += pj;
     const uint4 u = *reinterpret_cast<const uint4*>(vb + (size_t)j * ld);
     const float2 a = unpack16<FP16>(u.x), b = unpack16<FP16>(u.y), cc = unpack16<FP16>(u.z), d = unpack16<FP16>(u.w);

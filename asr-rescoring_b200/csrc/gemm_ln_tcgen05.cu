@@ -535,14 +535,15 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   const bool staged = K <= H;
   // cta_group::2 pairs inside the LayerNorm cluster (PLLB_LN_PAIR: 0 never, 1 default policy, 2 always,
   // 3 every mainloop-paced launch whatever the hidden size).
-  // Default: the mainloop-paced launches (K > H, i.e. FFN2) of the shapes whose doubled cluster still
-  // covers the chip — H = 256 (cluster 2: 148 SMs) and H = 768 (cluster 6: 132 of 148 SMs vs 135);
-  // H = 512 / 1024 would drop from 148 / 132 to 132 / 120 SMs.
+  // Default: the mainloop-paced launches (K > H, i.e. FFN2) for H = 256 (cluster 2: 148 SMs), H = 768
+  // (cluster 6: 132 SMs against 135; measured FFN2 -15.5 %, C2 step -3.0 %) and H = 1024 (cluster 8: 120
+  // SMs against 132; measured FFN2 -8.7 %, C4 step -2.0 %).  H = 512 would drop from 148 to 132 SMs
+  // and is left unpaired (no model of that width was measured).
   const char* pe = getenv("PLLB_LN_PAIR");
   const int pair_policy = pe ? atoi(pe) : 1;
   const int cn = H / BN;
   const bool pair = M > 2 * BM && (pair_policy == 2 || (pair_policy == 3 && !staged) ||
-                                   (pair_policy == 1 && !staged && (cn == 1 || cn == 3)));
+                                   (pair_policy == 1 && !staged && cn != 2));
   CUtensorMap ta, tb, t16;
   int rc;
   if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
