@@ -59,6 +59,7 @@ struct KParams {
   int M, N, K;
   const float* bias;
   LseArgs lse;
+  int early_release;
 };
 
 // HF activations "gelu" = nn.functional.gelu (erf form): 0.5 x (1 + erf(x / sqrt 2)).
@@ -261,6 +262,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cbase = (ew >> 2) * EPI_COLS;               // first tile column owned by this warp
     const uint32_t my_buf = sEpi + ew * EBUFS * EPI_BUF_BYTES;
     uint32_t acc = 0, acc_phase = 0, buf_i = 0;
+    // The accumulator buffer goes back to the MMA warp as soon as its last columns sit in registers
+    // (16-bit epilogues: before the bias / GELU math and the stores of the last 64 columns), not after
+    // them: PLLB_GEMM_EARLY_RELEASE=0 restores the late release.
+    const bool early_release = p.early_release != 0;
+    auto release_acc = [&]() {
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's MMA waits for both
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
+    };
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       const int m0 = PLLB_TILE_M(tile);
       const int tn = tile % tiles_n;
@@ -308,6 +321,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tmem_ld_32x32b_x32(t_addr + c0, r0);
           tmem_ld_32x32b_x32(t_addr + c0 + 32, r1);
           tcgen05_wait_ld();
+          if (early_release && c0 + 64 >= cbase + EPI_COLS) release_acc();   // last columns are in registers
           const uint32_t buf = my_buf + (buf_i % EBUFS) * EPI_BUF_BYTES;
           if (lane == 0) tma_store_wait_read<EBUFS - 1>();      // the store that last read this buffer is done
           __syncwarp();
@@ -378,12 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       // all tcgen05.ld of this accumulator have completed (wait::ld above): release it
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (TWO) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's MMA waits for both
-        else mbar_arrive(bar_tempty + 8 * acc);
-      }
+      if (!(early_release && (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16))) release_acc();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -463,7 +472,12 @@ int pair_mode(int epilogue) {
     if (v < -1 || v > 2) v = -1;
   }
   if (v >= 0) return v;
-  return epilogue == EPI_BIAS_GELU_BF16 ? 1 : 2;
+  if (epilogue == EPI_BIAS_GELU_BF16) {
+    const char* g = getenv("PLLB_GEMM_MODE_GELU");        // experiment knob: pair mode of the FFN1 launch alone
+    if (g && atoi(g) >= 0 && atoi(g) <= 2) return atoi(g);
+    return 1;
+  }
+  return 2;
 }
 
 }  // namespace
@@ -487,6 +501,7 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
   }
   KParams kp{};
   kp.M = (int)M; kp.N = N; kp.K = K; kp.bias = bias;
+  { const char* e = getenv("PLLB_GEMM_EARLY_RELEASE"); kp.early_release = e ? atoi(e) : 1; }
   if (epilogue == EPI_LSE) {
     if (!lse) return fail(PLLB_ERR_INVALID, "gemm: LSE epilogue needs LseArgs");
     kp.lse = *lse;
