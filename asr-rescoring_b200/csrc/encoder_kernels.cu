@@ -618,16 +618,20 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 // head) and are bound by instruction issue.  Kept as an opt-in (PLLB_ATT_TMA=1), bit-identical to
 // the default kernel.  One CTA walks over whole masked copies:
 //   warp 0        producer — per copy 3*NH TMA box loads (Q, K, V slice of every head: 64 columns x
-//                 R rows, R = T rounded up to 8, 128-byte swizzle) into a 2-stage ring, one mbarrier
-//                 transaction per stage; the next copy streams in while this one is computed, so
-//                 ~100 KB per SM is always in flight;
+//                 R rows, R = T rounded up to 8, 128-byte swizzle) into a byte-granular ring of
+//                 216 KiB with up to four copies in flight, one mbarrier transaction per copy; the
+//                 next copies stream in while this one is computed, so 100-200 KB per SM is always
+//                 in flight;
 //   warps 1..NH   one head each: ldmatrix from the swizzled tiles, the same 16x16 flash blocks on
 //                 mma.sync as above, context rows leave as 16-byte stores.
 // Copies longer than ATT_TMA_ROWS rows are left to attention_mma_kernel (launched with skip_le).
-constexpr int ATT_TMA_ROWS = 24;                    // rows per staged tile (T <= 24 covers 92 % of the C2 rows)
-constexpr int ATT_TMA_STAGES = 2;
-constexpr int ATT_TMA_MAPS = ATT_TMA_ROWS / 8;      // one tensor map per box height 8, 16, 24
-constexpr int ATT_TMA_MAX_HEADS = 12;               // 2 stages x 3*NH tiles x 24 rows x 128 B = 216 KiB at NH = 12
+constexpr int ATT_TMA_ROWS = 32;                    // longest copy it takes (T <= 32: all but 0.03 % of the C2 copies)
+constexpr int ATT_TMA_SLOTS = 4;                    // copies in flight (mbarrier pairs)
+constexpr int ATT_TMA_MAPS = ATT_TMA_ROWS / 8;      // one tensor map per box height 8, 16, 24, 32
+constexpr int ATT_TMA_MAX_HEADS = 12;
+// byte-granular ring: a copy of R = roundup8(T) rows occupies 3*NH*R*128 bytes (36 / 72 / 108 / 144 KiB at
+// NH = 12), placed back to back and wrapping to 0 when it does not fit
+constexpr int ATT_TMA_RING_BYTES = 3 * ATT_TMA_MAX_HEADS * 48 * 128;   // 216 KiB
 
 struct AttTmaMaps {
   CUtensorMap m[ATT_TMA_MAPS];
@@ -638,7 +642,7 @@ __device__ __forceinline__ uint32_t sw128(int row, int col) {
   return (uint32_t)(row * 128 + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2);
 }
 
-// One head of one copy from swizzled tiles of R rows (R % 8 == 0, T <= R <= 24).  Rows >= R do not
+// One head of one copy from swizzled tiles of R rows (R % 8 == 0, T <= R <= 32).  Rows >= R do not
 // exist: fragment loads clamp to the last row (their scores are masked / their p is 0) and the
 // output staging skips them.
 template <bool FP16>
@@ -775,12 +779,11 @@ attention_tma_kernel(const __grid_constant__ AttTmaMaps maps, __nv_bfloat16* __r
   extern __shared__ uint8_t att_tma_dyn[];
   const uint32_t raw = smem_u32(att_tma_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t stage_bytes = (uint32_t)(3 * NH * ATT_TMA_ROWS * 128);
-  const uint32_t bar_full = base + ATT_TMA_STAGES * stage_bytes;     // ATT_TMA_STAGES x 8 B
-  const uint32_t bar_empty = bar_full + 8 * ATT_TMA_STAGES;
+  const uint32_t bar_full = base + ATT_TMA_RING_BYTES;               // ATT_TMA_SLOTS x 8 B
+  const uint32_t bar_empty = bar_full + 8 * ATT_TMA_SLOTS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ATT_TMA_STAGES; ++s) {
+    for (int s = 0; s < ATT_TMA_SLOTS; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, (uint32_t)NH);
     }
@@ -789,21 +792,44 @@ attention_tma_kernel(const __grid_constant__ AttTmaMaps maps, __nv_bfloat16* __r
     for (int i = 0; i < ATT_TMA_MAPS; ++i) prefetch_tensormap(&maps.m[i]);
   }
   __syncthreads();
-  uint32_t stage = 0, phase = 0;
+  // Producer and consumers walk the same copies in the same order and place them identically:
+  // copy number i (of the accepted ones) uses barrier slot i % SLOTS and the byte range
+  // [off_i, off_i + size_i) with off_i = (cur + size_i <= RING) ? cur : 0.
+  const uint32_t row_bytes = (uint32_t)(3 * NH * 128);
+  uint32_t cur = 0;
+  int i = 0;
   if (warp == 0) {
     if (lane == 0) {
+      uint32_t beg[ATT_TMA_SLOTS] = {0, 0, 0, 0}, end[ATT_TMA_SLOTS] = {0, 0, 0, 0};   // ranges of the last SLOTS copies
       for (int c = blockIdx.x; c < n_copies; c += gridDim.x) {
         const int T = plan.seq_len[c];
         if (T > ATT_TMA_ROWS) continue;
         const int start = plan.seq_start[c];
         const int R = (T + 7) & ~7;
+        const uint32_t size = row_bytes * (uint32_t)R;
+        if (cur + size > (uint32_t)ATT_TMA_RING_BYTES) cur = 0;
+        const uint32_t off = cur;
+        cur += size;
+        const int slot = i % ATT_TMA_SLOTS;
+        // the slot's previous user (copy i - SLOTS) must be released ...
+        mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / ATT_TMA_SLOTS) & 1) ^ 1));
+        // ... and so must every younger copy whose bytes overlap the new range (releases are FIFO: the
+        // youngest overlapping one is enough)
+        for (int j = i - 1; j > i - ATT_TMA_SLOTS && j >= 0; --j) {
+          const int sj = j % ATT_TMA_SLOTS;
+          if (beg[sj] < off + size && off < end[sj]) {
+            mbar_wait(bar_empty + 8 * sj, (uint32_t)((j / ATT_TMA_SLOTS) & 1));
+            break;
+          }
+        }
+        beg[slot] = off;
+        end[slot] = off + size;
         const CUtensorMap* m = &maps.m[(R >> 3) - 1];
-        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(3 * NH * R * 128));
-        const uint32_t dst = base + stage * stage_bytes;
+        mbar_arrive_expect_tx(bar_full + 8 * slot, size);
+        const uint32_t dst = base + off;
         for (int sl = 0; sl < 3 * NH; ++sl)
-          tma_load_2d(dst + (uint32_t)(sl * R * 128), m, bar_full + 8 * stage, sl * 64, start);
-        if (++stage == ATT_TMA_STAGES) { stage = 0; phase ^= 1; }
+          tma_load_2d(dst + (uint32_t)(sl * R * 128), m, bar_full + 8 * slot, sl * 64, start);
+        ++i;
       }
     }
   } else if (warp <= NH) {
@@ -813,15 +839,19 @@ attention_tma_kernel(const __grid_constant__ AttTmaMaps maps, __nv_bfloat16* __r
       if (T > ATT_TMA_ROWS) continue;
       const int start = plan.seq_start[c];
       const int R = (T + 7) & ~7;
-      mbar_wait(bar_full + 8 * stage, phase);
+      const uint32_t size = row_bytes * (uint32_t)R;
+      if (cur + size > (uint32_t)ATT_TMA_RING_BYTES) cur = 0;
+      const uint32_t sb = base + cur;
+      cur += size;
+      const int slot = i % ATT_TMA_SLOTS;
+      mbar_wait(bar_full + 8 * slot, (uint32_t)((i / ATT_TMA_SLOTS) & 1));
       const uint32_t tile = (uint32_t)(R * 128);
-      const uint32_t sb = base + stage * stage_bytes;
       attn_compute_sw<FP16>(sb + (uint32_t)head * tile, sb + (uint32_t)(NH + head) * tile, sb + (uint32_t)(2 * NH + head) * tile,
                             ctx + (size_t)start * H + head * 64, T, R, H, lane);
       fence_proxy_async_smem();      // this warp wrote the tiles (zero fill, output staging) before the next TMA refill
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
-      if (++stage == ATT_TMA_STAGES) { stage = 0; phase ^= 1; }
+      if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+      ++i;
     }
   }
 }
@@ -1153,8 +1183,8 @@ int launch_attention(const void* qkv_bf16, void* ctx_bf16, CopyPlan plan, int32_
                            (uint32_t)(8 * (i + 1)), 64);
       if (rc) return rc;
     }
-    const int smem = ATT_TMA_STAGES * 3 * NH * ATT_TMA_ROWS * 128 + 16 * ATT_TMA_STAGES + 1024;
-    const int smem_max = ATT_TMA_STAGES * 3 * ATT_TMA_MAX_HEADS * ATT_TMA_ROWS * 128 + 16 * ATT_TMA_STAGES + 1024;
+    const int smem = ATT_TMA_RING_BYTES + 16 * ATT_TMA_SLOTS + 1024;
+    const int smem_max = smem;
     const int grid = (int)std::min<int64_t>(n_copies, sm_count());
     const int threads = 32 * (1 + NH);
     if (fp16) {

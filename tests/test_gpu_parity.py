@@ -742,16 +742,16 @@ def test_two_gpu_drop_in_outputs_identical_to_one_gpu():
 
 
 def test_tma_fed_attention_kernel_is_bit_identical(monkeypatch):
-    """PLLB_ATT_TMA=1 routes the copies of <= 24 rows through attention_tma_kernel (TMA box loads into
-    a 2-stage ring, producer warp + one warp per head): same blocks, same MMA order, so scores and
-    per-token terms must equal the default kernel's bit for bit — for 4, 8 and 12 heads, with
-    sequences on both sides of the 24-row limit."""
+    """PLLB_ATT_TMA=1 routes the copies of <= 32 rows through attention_tma_kernel (TMA box loads into
+    a byte-granular ring with up to four copies in flight, producer warp + one warp per head): same
+    blocks, same MMA order, so scores and per-token terms must equal the default kernel's bit for
+    bit — for 4, 8 and 12 heads, with sequences on both sides of the 32-row limit and many ring wraps."""
     rng = np.random.default_rng(11)
     for hidden, layers in ((256, 4), (512, 3), (768, 3)):
         cfg = dict(num_layers=layers, hidden=hidden, num_heads=hidden // 64, intermediate=2 * hidden, vocab=1500,
                    max_position=80, type_vocab=2, ln_eps=1e-12)
         sd = synth.random_init_state_dict(cfg, 5, perturb=True)
-        lens = [int(x) for x in rng.integers(1, 23, size=40)] + [22, 23, 24, 30, 47]
+        lens = [int(x) for x in rng.integers(1, 31, size=60)] + [22, 23, 24, 29, 30, 31, 47, 6, 30, 30, 1]
         off = np.zeros(len(lens) + 1, np.int64)
         np.cumsum(lens, out=off[1:])
         tok = rng.integers(104, cfg["vocab"], size=int(off[-1])).astype(np.int32)
