@@ -132,12 +132,17 @@ struct TimedLaunch {
 struct pllb_context {
   pllb_model_desc d{};
   int device = 0;
-  // operand types (pllb_model_desc.operand_dtype): 0 bf16 | 1 fp16 | 2 bf16 encoder + fp16 MLM head
-  bool fp16 = false;                 // encoder activations (hidden16, qkv, ctx, ffn) and weights are IEEE fp16, else bf16
+  // operand types (pllb_model_desc.operand_dtype): encoder layers l < fp16_from work on bf16
+  // activations and weights, layers l >= fp16_from on IEEE fp16; the MLM head is fp16 unless the
+  // whole model is bf16.  0 bf16 (fp16_from = NL, bf16 head) | 1 fp16 (0) | 2 bf16 encoder + fp16 head
+  // (NL) | 3 bf16 first half + fp16 second half and head (NL / 2) | 16 + k (k).
+  int fp16_from = 0;
   bool head_fp16 = false;            // the MLM head's activations and weights (transform, decoder) are fp16
-  int dt = DT_BF16;                  // GemmDtype of the encoder GEMMs
   int dt_head = DT_BF16;             // GemmDtype of the head transform + decoder
-  int dt_last = DT_BF16;             // GemmDtype of the pruned last layer's FFN2 (its 16-bit copy feeds the head)
+  bool lfp16(int l) const { return l >= fp16_from; }                       // layer l's 16-bit type is fp16
+  int ldt(int l) const { return lfp16(l) ? DT_FP16 : DT_BF16; }            // GemmDtype of layer l's GEMMs
+  // FFN2 of layer l writes the 16-bit copy that layer l + 1 (or the head) consumes: in THAT type
+  int ldt_ffn2(int l, bool next_fp16) const { return lfp16(l) ? DT_FP16 : (next_fp16 ? DT_BF16_OUT16 : DT_BF16); }
   bool has_head = false;             // MLM head weights were supplied (PLL scoring available)
   bool fused_ln = true;              // residual + LayerNorm inside the GEMM epilogue (PLLB_FUSED_LN=0 disables)
   bool prune_q = true;               // last layer: Q projection + attention for the consumed row only (PLLB_PRUNE_Q=0 disables)
@@ -207,10 +212,10 @@ int copy_f32(pllb_context* c, float** dst, const float* src, int64_t n, cudaStre
   return PLLB_OK;
 }
 
-int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n, cudaStream_t s) {
+int conv_16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n, bool fp16, cudaStream_t s) {
   int rc = dev_alloc(c, dst, n);
   if (rc) return rc;
-  return launch_f32_to_bf16(src, *dst, n, c->fp16, s);
+  return launch_f32_to_bf16(src, *dst, n, fp16, s);
 }
 
 #define RC(expr)            \
@@ -220,8 +225,7 @@ int conv_bf16(pllb_context* c, __nv_bfloat16** dst, const float* src, int64_t n,
   } while (0)
 
 int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const float* bias, void* C, int64_t M, int N,
-               int K, int epi, const LseArgs* lse, cudaStream_t s, int dt = -1) {
-  if (dt < 0) dt = c->dt;
+               int K, int epi, const LseArgs* lse, cudaStream_t s, int dt) {
   TimedLaunch* tl = nullptr;
   if (c->timing) {
     if (c->timed_used == c->timed.size()) {
@@ -245,9 +249,8 @@ int timed_gemm(pllb_context* c, int kind, const void* A, const void* W, const fl
 
 // GEMM + bias + residual + LayerNorm: fused kernel, or (PLLB_FUSED_LN=0) GEMM -> fp32 -> LayerNorm kernel.
 int timed_gemm_ln(pllb_context* c, int kind, const void* A, const void* W, const float* bias, const float* g,
-                  const float* be, float* hid32, void* hid16, int64_t M, int K, cudaStream_t s, int dt = -1) {
+                  const float* be, float* hid32, void* hid16, int64_t M, int K, cudaStream_t s, int dt) {
   const int H = c->d.hidden;
-  if (dt < 0) dt = c->dt;
   if (!c->fused_ln) {
     RC(timed_gemm(c, kind, A, W, bias, c->y_f32, M, H, K, EPI_BIAS_F32, nullptr, s, dt == DT_BF16_OUT16 ? DT_BF16 : dt));
     return launch_residual_ln(c->y_f32, hid32, hid16, g, be, c->d.ln_eps, M, H, (dt & 4) != 0, s);
@@ -294,12 +297,12 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
   if (share) {
     // unique embeddings: fp32 row-major in y_f32, 16-bit GEMM operand in ctx (free until attention writes it)
     RC(launch_embed_unique(tokens, tok_off, n_hyp, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b, d.ln_eps,
-                           H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->ctx, c->fp16, s));
+                           H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->ctx, c->lfp16(0), s));
     RC(launch_row_src(c->plan, n_copies, s));
     RC(launch_rowmajor_to_t32(c->y_f32, c->plan.row_src, c->hidden_f32, n_rows, H, s));
   } else {
     RC(launch_embed_ln(tokens, tok_off, c->plan, n_copies, c->word_emb, c->pos_emb, c->type_emb, c->emb_g, c->emb_b,
-                       d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->hidden_bf16, c->fp16, s));
+                       d.ln_eps, H, d.cls_id, d.sep_id, d.mask_id, d.vocab, c->y_f32, c->hidden_bf16, c->lfp16(0), s));
     RC(launch_rowmajor_to_t32(c->y_f32, nullptr, c->hidden_f32, n_rows, H, s));
   }
   // Only the [MASK] row of each copy reaches the MLM head (MLM_PLL/main.py:101), and after the
@@ -312,32 +315,36 @@ int run_chunk(pllb_context* c, const int32_t* tokens, const int32_t* tok_off, co
     const LayerDev& L = c->layers[l];
     const bool shared_rows = share && l == 0;
     const bool last = prune_last && l == n_layers - 1;
+    const bool f16 = c->lfp16(l);            // this layer's activations (hidden16, qkv, ctx, ffn) and weights
+    const int dt = c->ldt(l);
+    // type of the 16-bit copy this layer's FFN2 leaves behind: the next layer's, or the head's
+    const int dt_ffn2 = c->ldt_ffn2(l, l + 1 < d.num_layers ? c->lfp16(l + 1) : (cls ? f16 : c->head_fp16));
     if (last && !shared_rows && c->prune_q) {
       // The pruned last layer consumes one attention row per copy: K|V for every row, Q for that
       // row only (1/3 of the projection saved), then a single-query attention straight into hg.
       RC(timed_gemm(c, G_QKV, c->hidden_bf16, L.qkv_w + (size_t)H * H, L.qkv_b + H, c->wide, n_rows, 2 * H, H,
-                    EPI_BIAS_BF16, nullptr, s));
+                    EPI_BIAS_BF16, nullptr, s, dt));
       RC(launch_gather_rows_bf16(c->hidden_bf16, c->plan.mask_row, n_copies, H, c->hg, s));
-      RC(timed_gemm(c, G_QKV, c->hg, L.qkv_w, L.qkv_b, c->t_bf16, n_copies, H, H, EPI_BIAS_BF16, nullptr, s));
-      RC(launch_attention_row(c->t_bf16, c->wide, c->hg, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, s));
+      RC(timed_gemm(c, G_QKV, c->hg, L.qkv_w, L.qkv_b, c->t_bf16, n_copies, H, H, EPI_BIAS_BF16, nullptr, s, dt));
+      RC(launch_attention_row(c->t_bf16, c->wide, c->hg, c->plan, n_copies, H, d.num_heads, max_T, f16, s));
     } else {
       RC(timed_gemm(c, G_QKV, shared_rows ? c->ctx : c->hidden_bf16, L.qkv_w, L.qkv_b, c->wide,
-                    shared_rows ? n_unique : n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s));
-      RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, c->fp16, shared_rows, c->cap_rows, s));
+                    shared_rows ? n_unique : n_rows, 3 * H, H, EPI_BIAS_BF16, nullptr, s, dt));
+      RC(launch_attention(c->wide, c->ctx, c->plan, n_copies, H, d.num_heads, max_T, f16, shared_rows, c->cap_rows, s));
       if (last) RC(launch_gather_rows_bf16(c->ctx, c->plan.mask_row, n_copies, H, c->hg, s));
     }
     if (last) {
       RC(launch_gather_rows_f32(c->hidden_f32, c->plan.mask_row, n_copies, H, c->hid_c, s));
-      RC(timed_gemm_ln(c, G_AO, c->hg, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hid_c, c->t_bf16, n_copies, H, s));
-      RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
+      RC(timed_gemm_ln(c, G_AO, c->hg, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hid_c, c->t_bf16, n_copies, H, s, dt));
+      RC(timed_gemm(c, G_FF1, c->t_bf16, L.ff1_w, L.ff1_b, c->wide, n_copies, I, H, EPI_BIAS_GELU_BF16, nullptr, s, dt));
       // its 16-bit copy is the MLM head's input: written in the head's operand type
-      RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hid_c, c->t_bf16, n_copies, I, s,
-                       cls ? -1 : c->dt_last));
+      RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hid_c, c->t_bf16, n_copies, I, s, dt_ffn2));
       break;
     }
-    RC(timed_gemm_ln(c, G_AO, c->ctx, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hidden_f32, c->hidden_bf16, n_rows, H, s));
-    RC(timed_gemm(c, G_FF1, c->hidden_bf16, L.ff1_w, L.ff1_b, c->wide, n_rows, I, H, EPI_BIAS_GELU_BF16, nullptr, s));
-    RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hidden_f32, c->hidden_bf16, n_rows, I, s));
+    RC(timed_gemm_ln(c, G_AO, c->ctx, L.ao_w, L.ao_b, L.ao_g, L.ao_be, c->hidden_f32, c->hidden_bf16, n_rows, H, s, dt));
+    RC(timed_gemm(c, G_FF1, c->hidden_bf16, L.ff1_w, L.ff1_b, c->wide, n_rows, I, H, EPI_BIAS_GELU_BF16, nullptr, s, dt));
+    RC(timed_gemm_ln(c, G_FF2, c->wide, L.ff2_w, L.ff2_b, L.out_g, L.out_be, c->hidden_f32, c->hidden_bf16, n_rows, I, s,
+                     dt_ffn2));
   }
   if (upto_layer >= 0) return PLLB_OK;
   r_stage.next("stage3: head at the masked rows");
@@ -576,7 +583,7 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   const pllb_model_desc& d = *desc;
   if (d.hidden % 256 != 0 || d.hidden < 256 || d.hidden > 1024 || d.num_heads * 64 != d.hidden ||
       d.intermediate % 256 != 0 || d.num_layers < 1 || d.vocab < 1 || d.max_position < 3 ||
-      d.operand_dtype < 0 || d.operand_dtype > 2)
+      d.operand_dtype < 0 || (d.operand_dtype > 3 && (d.operand_dtype < 16 || d.operand_dtype > 16 + d.num_layers)))
     return fail(PLLB_ERR_INVALID, "unsupported model shape: need num_layers >= 1, hidden in {256,512,768,1024}, "
                                   "head dim 64, intermediate % 256 == 0");
   PLLB_CUDA(cudaSetDevice(device));
@@ -586,11 +593,10 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
   pllb_context* c = new pllb_context();
   c->d = d;
   c->device = device;
-  c->fp16 = d.operand_dtype == 1;
+  c->fp16_from = d.operand_dtype == 1 ? 0 : d.operand_dtype == 3 ? d.num_layers / 2
+               : d.operand_dtype >= 16 ? d.operand_dtype - 16 : d.num_layers;
   c->head_fp16 = d.operand_dtype >= 1;
-  c->dt = d.operand_dtype == 1 ? DT_FP16 : DT_BF16;
-  c->dt_head = d.operand_dtype >= 1 ? DT_FP16 : DT_BF16;
-  c->dt_last = d.operand_dtype == 1 ? DT_FP16 : d.operand_dtype == 2 ? DT_BF16_OUT16 : DT_BF16;
+  c->dt_head = c->head_fp16 ? DT_FP16 : DT_BF16;
   if (const char* e = getenv("PLLB_FUSED_LN")) c->fused_ln = atoi(e) != 0;
   if (const char* e = getenv("PLLB_SHARE_L0")) c->share_l0 = atoi(e) != 0;
   if (const char* e = getenv("PLLB_PRUNE_Q")) c->prune_q = atoi(e) != 0;
@@ -616,20 +622,20 @@ int pllb_create(pllb_handle* out, const pllb_model_desc* desc, const pllb_weight
     const pllb_layer_weights& lw = w->layers[l];
     LayerDev& L = c->layers[l];
     TRY(dev_alloc(c, &L.qkv_w, (int64_t)3 * H * H));
-    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->fp16, s));
-    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->fp16, s));
-    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->fp16, s));
+    TRY(launch_f32_to_bf16(lw.q_w, L.qkv_w, (int64_t)H * H, c->lfp16(l), s));
+    TRY(launch_f32_to_bf16(lw.k_w, L.qkv_w + (int64_t)H * H, (int64_t)H * H, c->lfp16(l), s));
+    TRY(launch_f32_to_bf16(lw.v_w, L.qkv_w + (int64_t)2 * H * H, (int64_t)H * H, c->lfp16(l), s));
     TRY(dev_alloc(c, &L.qkv_b, 3 * H));
     cudaMemcpyAsync(L.qkv_b, lw.q_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(L.qkv_b + H, lw.k_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(L.qkv_b + 2 * H, lw.v_b, sizeof(float) * H, cudaMemcpyDeviceToDevice, s);
-    TRY(conv_bf16(c, &L.ao_w, lw.ao_w, (int64_t)H * H, s));
+    TRY(conv_16(c, &L.ao_w, lw.ao_w, (int64_t)H * H, c->lfp16(l), s));
     TRY(copy_f32(c, &L.ao_b, lw.ao_b, H, s));
     TRY(copy_f32(c, &L.ao_g, lw.ao_ln_g, H, s));
     TRY(copy_f32(c, &L.ao_be, lw.ao_ln_b, H, s));
-    TRY(conv_bf16(c, &L.ff1_w, lw.ff1_w, (int64_t)I * H, s));
+    TRY(conv_16(c, &L.ff1_w, lw.ff1_w, (int64_t)I * H, c->lfp16(l), s));
     TRY(copy_f32(c, &L.ff1_b, lw.ff1_b, I, s));
-    TRY(conv_bf16(c, &L.ff2_w, lw.ff2_w, (int64_t)H * I, s));
+    TRY(conv_16(c, &L.ff2_w, lw.ff2_w, (int64_t)H * I, c->lfp16(l), s));
     TRY(copy_f32(c, &L.ff2_b, lw.ff2_b, H, s));
     TRY(copy_f32(c, &L.out_g, lw.out_ln_g, H, s));
     TRY(copy_f32(c, &L.out_be, lw.out_ln_b, H, s));

@@ -14,7 +14,16 @@ from . import _lib
 from ._lib import LayerWeights, ModelDesc, Stats, Weights, check
 
 VARIANTS = {"B": 0, "A": 1, "C": 2, 0: 0, 1: 1, 2: 2}
-OPERAND_DTYPES = {"bf16": 0, "fp16": 1, "bf16+fp16head": 2}   # pllb_model_desc.operand_dtype
+OPERAND_DTYPES = {"bf16": 0, "fp16": 1, "bf16+fp16head": 2, "bf16+fp16tail": 3}   # pllb_model_desc.operand_dtype
+
+
+def operand_dtype_code(name: str) -> int:
+    """"bf16" | "fp16" | "bf16+fp16head" (bf16 encoder, fp16 MLM head) | "bf16+fp16tail" (bf16 for the
+    first half of the encoder layers, fp16 for the second half and the head) | "fp16from:K" (bf16 for
+    layers < K, fp16 for layers >= K and the head)."""
+    if name.startswith("fp16from:"):
+        return 16 + int(name.split(":", 1)[1])
+    return OPERAND_DTYPES[name]
 # bf16 operands on every encoder GEMM and attention MMA (98.9 % of the FLOPs), IEEE fp16 operands on the
 # two MLM-head GEMMs: same speed as all-bf16 (measured), and the largest single rounding site is gone
 DEFAULT_OPERAND_DTYPE = "bf16+fp16head"
@@ -82,7 +91,7 @@ class PllScorer:
             w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
         d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
                       self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id,
-                      OPERAND_DTYPES[operand_dtype])
+                      operand_dtype_code(operand_dtype))
         self.operand_dtype = operand_dtype
         torch.cuda.synchronize(dev)
         check(self._lib.pllb_create(ctypes.byref(self._h), ctypes.byref(d), ctypes.byref(w), int(max_chunk_tokens), device))

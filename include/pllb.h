@@ -60,7 +60,11 @@ typedef struct pllb_model_desc {
                                  +-65504 instead of overflowing);
                              2 = bf16 encoder, fp16 MLM head (transform +
                                  decoder operands; 1 % of the FLOPs, removes
-                                 the largest single rounding site)           */
+                                 the largest single rounding site);
+                             3 = bf16 for encoder layers < NL/2, fp16 for the
+                                 layers >= NL/2 and the head;
+                             16 + k = bf16 for layers < k, fp16 from layer k on
+                                 and in the head (16 = mode 1, 16 + NL = mode 2) */
 } pllb_model_desc;
 
 /* One encoder layer; DEVICE pointers to fp32 tensors in nn.Linear layout
