@@ -51,15 +51,17 @@ def _layer_norm(x, g, b, eps):
 
 def bert_mlm_logits(sd: Dict[str, torch.Tensor], cfg: dict, input_ids: torch.Tensor,
                     attention_mask: torch.Tensor, upto_layer: int | None = None,
-                    return_hidden: bool = False) -> torch.Tensor:
-    """fp32 BertForMaskedLM.forward(...).logits — modeling_bert.py:944-987."""
+                    return_hidden: bool = False, padding_idx: int | None = None) -> torch.Tensor:
+    """fp32 BertForMaskedLM.forward(...).logits — modeling_bert.py:944-987.
+    padding_idx: nn.Embedding(..., padding_idx=pad_token_id) (:75) — same forward; under autograd the
+    lookup contributes no gradient to that row (training oracle only)."""
     B, T = input_ids.shape
     H, NH = cfg["hidden"], cfg["num_heads"]
     dh = H // NH
     eps = cfg.get("ln_eps", 1e-12)
     pos = torch.arange(T)
     # BertEmbeddings (:72-112): word + token_type(0) + position -> LayerNorm
-    x = (sd["bert.embeddings.word_embeddings.weight"][input_ids]
+    x = (F.embedding(input_ids, sd["bert.embeddings.word_embeddings.weight"], padding_idx=padding_idx)
          + sd["bert.embeddings.token_type_embeddings.weight"][0]
          + sd["bert.embeddings.position_embeddings.weight"][pos])
     x = _layer_norm(x, sd["bert.embeddings.LayerNorm.weight"], sd["bert.embeddings.LayerNorm.bias"], eps)

@@ -636,7 +636,8 @@ def test_config4_24_layers_L64_vs_reference_golden(gold_dir):
     assert L.max() == 64 and L.min() == 8 and len(L) >= 40 and gold["cfg"]["num_layers"] == 24
     sd = synth.random_init_state_dict(gold["cfg"], gold["seed"])
     err = {}
-    for mode in ("fp16", "bf16+fp16head", "bf16"):
+    extra = [m for m in os.environ.get("PLLB_C4_GOLDEN_MODES", "").split(",") if m]   # measured and printed only
+    for mode in ["fp16", "bf16+fp16head", "bf16"] + extra:
         with engine.PllScorer(sd, gold["cfg"], operand_dtype=mode, max_chunk_tokens=1 << 16) as sc:
             err[mode] = np.abs(sc.score_packed(tok, off) - ref)
         print(f"c4 golden, {mode}: max |dPLL| {err[mode].max():.4f}, mean {err[mode].mean():.4f}, "
