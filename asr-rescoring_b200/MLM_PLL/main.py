@@ -1,23 +1,30 @@
-"""Drop-in for the scoring path of the reference's ``MLM_PLL/main.py``.
+"""Drop-in for the reference's ``MLM_PLL/main.py``: PLL scoring and MLM fine-tuning.
 
     cd MLM_PLL && python main.py --config config/score.yaml
+    cd MLM_PLL && python main.py --config config/train.yaml
 
-Same ``--config`` flag, same YAML keys (MLM_PLL/config/score.yaml:1-20), same output files
-(``<output_path>{train,dev,test}_lm.json``: {utt_id: {hyp_id: float}}, indent=4,
-ensure_ascii=False).  Differences, each deliberate (SURVEY.md §8a "quirks"):
+Same ``--config`` flag, same YAML keys (MLM_PLL/config/score.yaml:1-20, train.yaml:1-25), same output
+files (``<output_path>{train,dev,test}_lm.json``: {utt_id: {hyp_id: float}}, indent=4,
+ensure_ascii=False; ``<output_path>/checkpoint_<epoch>.pth`` and ``<output_path>/loss.json`` for
+training).  Differences, each deliberate (SURVEY.md §8a "quirks"):
 
 * all three splits are scored — the reference's dev/test blocks sit inside a string
   literal (MLM_PLL/main.py:205-238) although rescore.py consumes their outputs;
 * the arithmetic runs in libpllb200.so on a B200 (no padding, no [copies x T x V] logits,
-  no per-batch host syncs); there is no CPU fallback and ``task: training``
-  (MLM_PLL/main.py:117-161) is out of scope;
+  no per-batch host syncs); there is no CPU fallback;
+* ``task: training`` (MLM_PLL/main.py:117-161) runs on the same library (engine.MlmTrainer: forward,
+  backward and AdamW as CUDA kernels).  The reference starts from the hub checkpoint
+  (``from_pretrained(config.model.bert)``, :128); offline the starting weights come from
+  ``model.pretrained_path`` (a state_dict file) or ``model.random_init_seed``.  Dropout masks come
+  from the library's own counter-based generator, not torch's RNG;
 * data files may be the reference's row-list JSON (MLM_PLL/preprocess.py:9-30), a
   ``hyps_text.json`` ({utt: {hyp: str}}, tokenised here) or the compact packed JSON that
   our ``preprocess.py`` writes — the O(sum L^2) row list is never needed;
 * optional keys (absent from the reference YAMLs, all defaulted): ``model.vocab_path``,
   ``model.random_init_seed``, ``model.operand_dtype`` ("bf16+fp16head" default: bf16 encoder,
   fp16 MLM head | "bf16" | "fp16": 8x smaller rounding error, ~5 % slower, needed for 24-layer
-  encoders at L > ~40), ``max_chunk_tokens``.
+  encoders at L > ~40), ``max_chunk_tokens``; training: ``model.pretrained_path``,
+  ``model.hidden_dropout_prob`` / ``model.attention_probs_dropout_prob`` (0.1 = BertConfig default).
 """
 from __future__ import annotations
 
@@ -34,10 +41,10 @@ if _PKG_PARENT not in sys.path:
     sys.path.insert(0, _PKG_PARENT)
 
 from asr_rescoring_b200 import shard, synth  # noqa: E402
-from asr_rescoring_b200.engine import DEFAULT_OPERAND_DTYPE, PllScorer  # noqa: E402
+from asr_rescoring_b200.engine import DEFAULT_OPERAND_DTYPE, MlmTrainer, PllScorer  # noqa: E402
 from asr_rescoring_b200.tokenizer import BertCharTokenizer, SyntheticCharTokenizer, encode_batch  # noqa: E402
 from asr_rescoring_b200.util.arg_parser import ArgParser  # noqa: E402
-from asr_rescoring_b200.util.saving import json_saving  # noqa: E402
+from asr_rescoring_b200.util.saving import json_saving, model_saving  # noqa: E402
 
 MODEL_SHAPES = {"bert-base-chinese": synth.BERT_BASE_CHINESE, "bert-large-shaped": synth.BERT_LARGE_SHAPED,
                 "bert-tiny-test": synth.BERT_TINY}
@@ -62,28 +69,56 @@ def collate(batch: List[dict]):
     return list(batch)
 
 
-class RowLoader:
-    """Sequential batches of rows (shuffle=False as for scoring, MLM_PLL/main.py:58-61)."""
+def pad_batch(batch: List[dict]):
+    """The arrays the reference's collate builds (MLM_PLL/main.py:28-54, pad_sequence(batch_first=True)):
+    input_ids, attention_mask, labels as int32 [B, Tmax], right-padded with 0."""
+    T = max(len(r["input_ids"]) for r in batch)
+    ids = np.zeros((len(batch), T), np.int32)
+    am = np.zeros((len(batch), T), np.int32)
+    lab = np.zeros((len(batch), T), np.int32)
+    for i, r in enumerate(batch):
+        ids[i, :len(r["input_ids"])] = r["input_ids"]
+        am[i, :len(r["attention_masks"])] = r["attention_masks"]
+        lab[i, :len(r["labels"])] = r["labels"]
+    return ids, am, lab
 
-    def __init__(self, dataset, batch_size: int):
+
+class RowLoader:
+    """Batches of rows in DataLoader order (MLM_PLL/main.py:57-70): sequential, or — shuffle=True — a
+    fresh permutation per epoch drawn the way torch's RandomSampler draws it (a generator seeded from
+    torch's global RNG, then randperm), so ``torch.manual_seed(config.seed)`` (MLM_PLL/main.py:245-247)
+    fixes the order exactly as it does for the reference."""
+
+    def __init__(self, dataset, batch_size: int, shuffle: bool = False):
         self.dataset = dataset
         self.batch_size = max(int(batch_size), 1)
+        self.shuffle = bool(shuffle)
 
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
-        for s in range(0, len(self.dataset), self.batch_size):
-            yield collate(self.dataset[s:s + self.batch_size])
+        if not self.shuffle:
+            for s in range(0, len(self.dataset), self.batch_size):
+                yield collate(self.dataset[s:s + self.batch_size])
+            return
+        import torch
+        # torch 2.x DataLoader: the iterator first draws its worker base seed from the global RNG
+        # (_BaseDataLoaderIter.__init__), then RandomSampler draws the seed of its own generator
+        torch.empty((), dtype=torch.int64).random_()
+        g = torch.Generator()
+        g.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+        order = torch.randperm(len(self.dataset), generator=g).tolist()
+        for s in range(0, len(order), self.batch_size):
+            yield collate([self.dataset[i] for i in order[s:s + self.batch_size]])
 
 
 def set_dataloader(config, dataset, for_scoring=False):
     """MLM_PLL/main.py:57-70.  ``num_worker`` host processes are not needed (no tensors are
     built on the host); the key is still read so a YAML without it fails as before."""
     _ = config.num_worker
-    if not for_scoring:
-        raise NotImplementedError("only the scoring path (for_scoring=True) is implemented")
-    return RowLoader(dataset, config.batch_size)
+    shuffle = False if for_scoring else config.shuffle
+    return RowLoader(dataset, config.batch_size, shuffle)
 
 
 def _iter_rows(dataloader) -> Iterable[dict]:
@@ -95,14 +130,33 @@ def _iter_rows(dataloader) -> Iterable[dict]:
                 yield row
 
 
-def run_one_epoch(config, model: PllScorer, dataloader, output_score=None, train_mode=True, do_scoring=False):
-    """Scoring branch of MLM_PLL/main.py:73-114: for every row (one masked copy) add
+def _run_loss_epoch(config, model: MlmTrainer, dataloader, train_mode: bool) -> float:
+    """run_one_epoch with do_scoring=False (MLM_PLL/main.py:73-99,109-112): the mean of the batch
+    losses; train_mode adds backward + AdamW per batch, with a fresh optimizer per epoch (:76)."""
+    if not isinstance(model, MlmTrainer):
+        raise TypeError("the training / loss pass needs an engine.MlmTrainer (build_trainer), not a PllScorer")
+    if train_mode:
+        model.reset_optimizer(config.lr)
+    epoch_loss, n_batches = 0.0, 0
+    for batch in dataloader:
+        ids, am, lab = pad_batch(batch)
+        epoch_loss += model.step(ids, am, lab, mode=1 if train_mode else 0)
+        n_batches += 1
+    return epoch_loss / len(dataloader) if n_batches else 0.0
+
+
+def run_one_epoch(config, model, dataloader, output_score=None, train_mode=True, do_scoring=False):
+    """MLM_PLL/main.py:73-114.  do_scoring=False: the fine-tuning / dev-loss pass (model is an
+    engine.MlmTrainer), returns the epoch loss.  Scoring branch: for every row (one masked copy) add
     log_softmax(logits[mask_pos])[labels[mask_pos]] to output_score[utt_id][hyp_id].
     Rows of one hypothesis are consecutive (preprocess.py emits them so); a row list cut in
     the middle of a hypothesis by ``num_of_data`` adds only the rows present, like the
     reference."""
-    if train_mode or not do_scoring:
-        raise NotImplementedError("MLM fine-tuning (MLM_PLL/main.py:96-99,117-161) is out of scope")
+    if not do_scoring:
+        return _run_loss_epoch(config, model, dataloader, train_mode)
+    if train_mode:
+        raise NotImplementedError("scoring while training (train_mode and do_scoring both set) is never used by the "
+                                  "reference's drivers (MLM_PLL/main.py:135-153,194-201) and is not implemented")
     groups: List[Tuple[str, str, List[int], List[int]]] = []   # utt, hyp, tokens, mask positions present
     last_key = None
     for row in _iter_rows(dataloader):
@@ -276,8 +330,52 @@ def pll_bert_scoring(config):
         dist.destroy_process_group()
 
 
+def build_trainer(config, device: int = 0, max_rows: int = 0, max_seq: int = 0) -> MlmTrainer:
+    """Replaces BertForMaskedLM.from_pretrained(config.model.bert).to(device) (MLM_PLL/main.py:128-129).
+    The hub is not reachable offline: the starting state_dict comes from ``model.pretrained_path`` or,
+    for synthetic runs, ``model.random_init_seed``."""
+    import torch
+    path = getattr(config.model, "pretrained_path", None)
+    seed = getattr(config.model, "random_init_seed", None)
+    if path and os.path.exists(path):
+        sd = torch.load(path, map_location="cpu")
+        cfg = synth.config_from_state_dict(sd)
+    elif seed is not None:
+        cfg = MODEL_SHAPES[config.model.bert]
+        sd = synth.random_init_state_dict(cfg, int(seed))
+    else:
+        raise FileNotFoundError(f"model.pretrained_path {path!r} not found and model.random_init_seed not set "
+                                f"(the reference downloads {config.model.bert!r} from the hub)")
+    return MlmTrainer(sd, cfg, device=device, lr=float(config.lr),
+                      hidden_dropout=float(getattr(config.model, "hidden_dropout_prob", 0.1)),
+                      attention_dropout=float(getattr(config.model, "attention_probs_dropout_prob", 0.1)),
+                      seed=int(config.seed or 0), max_rows=max_rows or 4096, max_seq=max_seq or 128)
+
+
 def mlm_finetune_bert(config):
-    raise NotImplementedError("task 'training' (MLM_PLL/main.py:117-161) is out of scope of the B200 scoring path")
+    """MLM_PLL/main.py:117-161: per epoch one training pass, one dev-loss pass, a checkpoint
+    (<output_path>/checkpoint_<epoch>.pth, the bare state_dict) and <output_path>/loss.json."""
+    train_set = MyDataset(json.load(open(config.train_data_path, "r", encoding="utf-8")))[:config.num_of_data]
+    dev_set = MyDataset(json.load(open(config.dev_data_path, "r", encoding="utf-8")))[:config.num_of_data]
+    train_loader = set_dataloader(config.dataloader, train_set, False)
+    dev_loader = set_dataloader(config.dataloader, dev_set, True)
+    dev = config.device
+    longest = max([len(r["input_ids"]) for r in train_set] + [len(r["input_ids"]) for r in dev_set] + [1])
+    model = build_trainer(config, int(str(dev).split(":")[1]) if ":" in str(dev) else 0,
+                          max_rows=int(config.dataloader.batch_size) * longest, max_seq=longest)
+    train_loss_record = [0] * config.epoch
+    dev_loss_record = [0] * config.epoch
+    for epoch_id in range(1, config.epoch + 1):
+        print("Epoch {}/{}".format(epoch_id, config.epoch))
+        train_loss_record[epoch_id - 1] = run_one_epoch(config=config, model=model, output_score=None,
+                                                        dataloader=train_loader, train_mode=True, do_scoring=False)
+        print("epoch ", epoch_id, " train loss: ", train_loss_record[epoch_id - 1])
+        dev_loss_record[epoch_id - 1] = run_one_epoch(config=config, model=model, output_score=None,
+                                                      dataloader=dev_loader, train_mode=False, do_scoring=False)
+        print("epoch ", epoch_id, " dev loss: ", dev_loss_record[epoch_id - 1], "\n")
+        model_saving(config.output_path, model.state_dict(), epoch_id)
+        json_saving(config.output_path + "/loss.json", {"train": train_loss_record, "dev": dev_loss_record})
+    model.close()
 
 
 if __name__ == "__main__":

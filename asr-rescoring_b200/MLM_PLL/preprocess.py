@@ -1,10 +1,12 @@
-"""Drop-in for the ``for_scoring`` jobs of the reference's ``MLM_PLL/preprocess.py``.
+"""Drop-in for the reference's ``MLM_PLL/preprocess.py`` (the for_training and for_scoring jobs).
 
 The reference materialises every masked copy as a JSON row (O(sum L^2) integers,
 MLM_PLL/preprocess.py:9-30); here the expansion happens on the GPU (stage 1 of
 libpllb200), so preprocessing only tokenises each hypothesis once and writes a compact
 packed file.  ``do_job`` is kept with the reference's signature and row schema for callers
 that still want rows (it is what the parity tests compare the device expansion against).
+The two ``for_training`` jobs (preprocess.py:36-44, over ref_text.json) do write the reference's row
+list: the fine-tuning loss needs every masked copy as a batch row (MLM_PLL/main.py:117-161).
 """
 from __future__ import annotations
 
@@ -74,6 +76,8 @@ if __name__ == "__main__":
         raise SystemExit("preprocess.py: set PLLB_VOCAB=<path to bert-base-chinese vocab.txt> "
                          "(or PLLB_SYNTHETIC_TOKENIZER=1 for random-init experiments)")
     jobs = [
+        {"task": "for_training", "in": "../espnet_data/alfred/train/ref_text.json", "out": "preprocessed_data/for_training/train.json"},
+        {"task": "for_training", "in": "../espnet_data/alfred/dev/ref_text.json", "out": "preprocessed_data/for_training/dev.json"},
         {"task": "for_scoring", "in": "../espnet_data/alfred/train/hyps_text.json", "out": "preprocessed_data/for_scoring/train.json"},
         {"task": "for_scoring", "in": "../espnet_data/alfred/dev/hyps_text.json", "out": "preprocessed_data/for_scoring/dev.json"},
         {"task": "for_scoring", "in": "../espnet_data/alfred/test/hyps_text.json", "out": "preprocessed_data/for_scoring/test.json"},
@@ -81,4 +85,10 @@ if __name__ == "__main__":
     for job in jobs:
         json_data = json.load(open(job["in"], "r", encoding="utf-8"))
         os.makedirs(os.path.dirname(job["out"]), exist_ok=True)
-        json_saving(job["out"], pack_hyps_text(json_data, bert_tokenizer))
+        if job["task"] == "for_training":            # preprocess.py:58-60: rows of the reference sentences, hyp_id None
+            output_json = []
+            for utt_id, sentence in json_data.items():
+                output_json = do_job(sentence, utt_id, None, job["task"], output_json)
+            json_saving(job["out"], output_json)
+        else:
+            json_saving(job["out"], pack_hyps_text(json_data, bert_tokenizer))

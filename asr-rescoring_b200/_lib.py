@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint16, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint16, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PLLB_LIB") or os.path.join(HERE, "libpllb200.so")   # PLLB_LIB: A/B testing of builds
@@ -43,6 +43,12 @@ class Stats(ctypes.Structure):
                 ("last_gemm_ms", c_float), ("last_total_ms", c_float), ("last_gemm_launches", c_int64)]
 
 
+class TrainDesc(ctypes.Structure):
+    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("adam_eps", c_float), ("weight_decay", c_float),
+                ("hidden_dropout", c_float), ("attention_dropout", c_float), ("seed", c_uint64), ("pad_id", c_int32),
+                ("max_rows", c_int32), ("max_seq", c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/pllb.h declares
 SIGNATURES = {
     "pllb_last_error": (c_char_p, []),
@@ -73,6 +79,14 @@ SIGNATURES = {
     "pllb_rescore_sweep_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
                                         c_int32, c_void_p, c_void_p]),
     "pllb_rescore_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_double, c_int32, c_void_p, c_void_p]),
+    "pllb_train_create": (c_int, [POINTER(c_void_p), POINTER(ModelDesc), POINTER(Weights), POINTER(TrainDesc), c_int]),
+    "pllb_train_destroy": (c_int, [c_void_p]),
+    "pllb_train_workspace_bytes": (c_int64, [c_void_p]),
+    "pllb_train_kernel_launches": (c_int64, [c_void_p]),
+    "pllb_train_reset_optimizer": (c_int, [c_void_p, c_float]),
+    "pllb_train_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_float)]),
+    "pllb_train_export": (c_int, [c_void_p, POINTER(Weights)]),
+    "pllb_train_export_grads": (c_int, [c_void_p, POINTER(Weights)]),
 }
 
 _lib = None

@@ -17,6 +17,8 @@ UNITS = {
     "gemm_tcgen05.cu": [],
     "gemm_ln_tcgen05.cu": [],
     "encoder_kernels.cu": [],
+    "train_kernels.cu": [],
+    "train_api.cu": [],
     # fp64 combiner must round like numpy: no FMA contraction, IEEE division
     "rescore_kernels.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
 }

@@ -34,6 +34,49 @@ def _np_ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def weights_struct(get, num_layers: int, keys):
+    """pllb_weights over the tensors ``get(key)`` returns (CUDA fp32, contiguous) for the HF
+    BertForMaskedLM state_dict names.  Returns (struct, list keeping the tensors and the layer array
+    alive).  The MLM head is optional: a RescoreBert checkpoint (BertModel + Linear(H, 1)) has none."""
+    keys = set(keys)
+    keep = []
+
+    def dp(key):
+        t = get(key)
+        keep.append(t)
+        return ctypes.c_void_p(t.data_ptr())
+
+    layers = (LayerWeights * max(num_layers, 1))()
+    keep.append(layers)
+    for i in range(num_layers):
+        p = f"bert.encoder.layer.{i}."
+        lw = layers[i]
+        lw.q_w, lw.q_b = dp(p + "attention.self.query.weight"), dp(p + "attention.self.query.bias")
+        lw.k_w, lw.k_b = dp(p + "attention.self.key.weight"), dp(p + "attention.self.key.bias")
+        lw.v_w, lw.v_b = dp(p + "attention.self.value.weight"), dp(p + "attention.self.value.bias")
+        lw.ao_w, lw.ao_b = dp(p + "attention.output.dense.weight"), dp(p + "attention.output.dense.bias")
+        lw.ao_ln_g, lw.ao_ln_b = dp(p + "attention.output.LayerNorm.weight"), dp(p + "attention.output.LayerNorm.bias")
+        lw.ff1_w, lw.ff1_b = dp(p + "intermediate.dense.weight"), dp(p + "intermediate.dense.bias")
+        lw.ff2_w, lw.ff2_b = dp(p + "output.dense.weight"), dp(p + "output.dense.bias")
+        lw.out_ln_g, lw.out_ln_b = dp(p + "output.LayerNorm.weight"), dp(p + "output.LayerNorm.bias")
+    w = Weights()
+    w.word_emb = dp("bert.embeddings.word_embeddings.weight")
+    w.pos_emb = dp("bert.embeddings.position_embeddings.weight")
+    w.type_emb = dp("bert.embeddings.token_type_embeddings.weight")
+    w.emb_ln_g = dp("bert.embeddings.LayerNorm.weight")
+    w.emb_ln_b = dp("bert.embeddings.LayerNorm.bias")
+    w.layers = ctypes.cast(layers, ctypes.POINTER(LayerWeights))
+    if "cls.predictions.transform.dense.weight" in keys:
+        w.head_w = dp("cls.predictions.transform.dense.weight")
+        w.head_b = dp("cls.predictions.transform.dense.bias")
+        w.head_ln_g = dp("cls.predictions.transform.LayerNorm.weight")
+        w.head_ln_b = dp("cls.predictions.transform.LayerNorm.bias")
+        w.decoder_w = dp("cls.predictions.decoder.weight" if "cls.predictions.decoder.weight" in keys
+                         else "bert.embeddings.word_embeddings.weight")
+        w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in keys else "cls.predictions.decoder.bias")
+    return w, keep
+
+
 class PllScorer:
     """BERT masked-LM pseudo-log-likelihood scorer; stands in for the
     ``BertForMaskedLM`` + ``run_one_epoch(do_scoring=True)`` pair of
@@ -51,44 +94,10 @@ class PllScorer:
         self.cfg = dict(cfg) if cfg is not None else config_from_state_dict(state_dict)
         self.device = device
         dev = torch.device("cuda", device)
-        keep = []
-
-        def dp(key):
-            t = state_dict[key].detach().to(device=dev, dtype=torch.float32).contiguous()
-            keep.append(t)
-            return ctypes.c_void_p(t.data_ptr())
-
         nl = self.cfg["num_layers"]
-        layers = (LayerWeights * max(nl, 1))()
-        for i in range(nl):
-            p = f"bert.encoder.layer.{i}."
-            lw = layers[i]
-            lw.q_w, lw.q_b = dp(p + "attention.self.query.weight"), dp(p + "attention.self.query.bias")
-            lw.k_w, lw.k_b = dp(p + "attention.self.key.weight"), dp(p + "attention.self.key.bias")
-            lw.v_w, lw.v_b = dp(p + "attention.self.value.weight"), dp(p + "attention.self.value.bias")
-            lw.ao_w, lw.ao_b = dp(p + "attention.output.dense.weight"), dp(p + "attention.output.dense.bias")
-            lw.ao_ln_g, lw.ao_ln_b = dp(p + "attention.output.LayerNorm.weight"), dp(p + "attention.output.LayerNorm.bias")
-            lw.ff1_w, lw.ff1_b = dp(p + "intermediate.dense.weight"), dp(p + "intermediate.dense.bias")
-            lw.ff2_w, lw.ff2_b = dp(p + "output.dense.weight"), dp(p + "output.dense.bias")
-            lw.out_ln_g, lw.out_ln_b = dp(p + "output.LayerNorm.weight"), dp(p + "output.LayerNorm.bias")
-        w = Weights()
-        w.word_emb = dp("bert.embeddings.word_embeddings.weight")
-        w.pos_emb = dp("bert.embeddings.position_embeddings.weight")
-        w.type_emb = dp("bert.embeddings.token_type_embeddings.weight")
-        w.emb_ln_g = dp("bert.embeddings.LayerNorm.weight")
-        w.emb_ln_b = dp("bert.embeddings.LayerNorm.bias")
-        w.layers = ctypes.cast(layers, ctypes.POINTER(LayerWeights))
-        # the MLM head is optional: a RescoreBert checkpoint (BertModel + Linear(H, 1)) has none
-        self.has_mlm_head = "cls.predictions.transform.dense.weight" in state_dict
-        if self.has_mlm_head:
-            w.head_w = dp("cls.predictions.transform.dense.weight")
-            w.head_b = dp("cls.predictions.transform.dense.bias")
-            w.head_ln_g = dp("cls.predictions.transform.LayerNorm.weight")
-            w.head_ln_b = dp("cls.predictions.transform.LayerNorm.bias")
-            dec_w = "cls.predictions.decoder.weight" if "cls.predictions.decoder.weight" in state_dict \
-                else "bert.embeddings.word_embeddings.weight"
-            w.decoder_w = dp(dec_w)
-            w.decoder_b = dp("cls.predictions.bias" if "cls.predictions.bias" in state_dict else "cls.predictions.decoder.bias")
+        w, keep = weights_struct(lambda key: state_dict[key].detach().to(device=dev, dtype=torch.float32).contiguous(),
+                                 nl, state_dict.keys())
+        self.has_mlm_head = bool(w.head_w)
         d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
                       self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), cls_id, sep_id, mask_id,
                       operand_dtype_code(operand_dtype))
@@ -233,6 +242,126 @@ class PllScorer:
         d["gemm_flops_by_kind"] = dict(zip(GEMM_KINDS, [float(x) for x in fl]))
         d["workspace_bytes"] = int(self._lib.pllb_workspace_bytes(self._h))
         return d
+
+
+class MlmTrainer:
+    """BERT masked-LM fine-tuning on the device; stands in for ``BertForMaskedLM`` (train mode) +
+    ``torch.optim.AdamW`` inside ``run_one_epoch(train_mode=True)`` (MLM_PLL/main.py:73-99) and for
+    the loss-only dev pass (train_mode=False, do_scoring=False).  fp32 master weights, bf16 GEMM
+    operands, fp32 accumulation.  ``hidden_dropout`` / ``attention_dropout`` default to the
+    BertConfig values of bert-base-chinese (0.1); the masks come from a stateless hash of
+    (seed, step, site, element), not from torch's RNG, so only runs with dropout 0 are comparable
+    value by value with the reference."""
+
+    TIED = {"cls.predictions.decoder.weight": "bert.embeddings.word_embeddings.weight",
+            "cls.predictions.decoder.bias": "cls.predictions.bias"}
+
+    def __init__(self, state_dict: Dict[str, "torch.Tensor"], cfg: Optional[dict] = None, device: int = 0,
+                 lr: float = 1e-5, hidden_dropout: float = 0.1, attention_dropout: float = 0.1, seed: int = 0,
+                 max_rows: int = 4096, max_seq: int = 128, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.01, pad_id: int = 0):
+        import torch
+        from ._lib import TrainDesc
+        from .synth import config_from_state_dict
+
+        self._lib = _lib.load()
+        _lib.require_device()
+        self._h = ctypes.c_void_p()
+        self.cfg = dict(cfg) if cfg is not None else config_from_state_dict(state_dict)
+        self.device = device
+        self._dev = torch.device("cuda", device)
+        if "cls.predictions.transform.dense.weight" not in state_dict:
+            raise ValueError("MLM fine-tuning needs a BertForMaskedLM state_dict (cls.predictions.* missing)")
+        self._keys = [k for k in state_dict.keys()]
+        self._passthrough = {k: v for k, v in state_dict.items() if k.endswith("position_ids")}
+        self._shapes = {k: tuple(v.shape) for k, v in state_dict.items()}
+        nl = self.cfg["num_layers"]
+        self.max_seq = min(int(max_seq), int(self.cfg["max_position"]), 512)
+        w, keep = weights_struct(lambda key: state_dict[key].detach().to(device=self._dev, dtype=torch.float32).contiguous(),
+                                 nl, state_dict.keys())
+        d = ModelDesc(nl, self.cfg["hidden"], self.cfg["num_heads"], self.cfg["intermediate"], self.cfg["vocab"],
+                      self.cfg["max_position"], float(self.cfg.get("ln_eps", 1e-12)), 101, 102, 103, 0)
+        td = TrainDesc(float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(hidden_dropout),
+                       float(attention_dropout), int(seed) & (2 ** 64 - 1), int(pad_id), int(max_rows), self.max_seq)
+        torch.cuda.synchronize(self._dev)
+        check(self._lib.pllb_train_create(ctypes.byref(self._h), ctypes.byref(d), ctypes.byref(w), ctypes.byref(td), device))
+        del keep
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pllb_train_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset_optimizer(self, lr: float):
+        """A fresh AdamW, as the reference creates one per epoch (MLM_PLL/main.py:76)."""
+        check(self._lib.pllb_train_reset_optimizer(self._h, float(lr)))
+
+    def step(self, input_ids, attention_mask, labels, mode: int = 1) -> float:
+        """One zero-padded batch (int arrays [B, T], what collate builds).  mode 1: forward + backward
+        + AdamW step; 0: loss only (eval); 2: forward + backward without the update.  Returns the loss."""
+        ids = np.ascontiguousarray(input_ids, np.int32)
+        lab = np.ascontiguousarray(labels, np.int32)
+        am = np.asarray(attention_mask)
+        if ids.ndim != 2 or lab.shape != ids.shape or am.shape != ids.shape:
+            raise ValueError("input_ids, attention_mask and labels must be equal [B, T] arrays")
+        nv = np.ascontiguousarray((am != 0).sum(1), np.int32)
+        if ((am != 0) != (np.arange(ids.shape[1])[None, :] < nv[:, None])).any():
+            raise ValueError("attention_mask must be a prefix mask (ones, then the zero padding of collate)")
+        loss = ctypes.c_float(0.0)
+        check(self._lib.pllb_train_step_host(self._h, _np_ptr(ids), _np_ptr(nv), _np_ptr(lab), ids.shape[0], ids.shape[1],
+                                             int(mode), ctypes.byref(loss)))
+        return float(loss.value)
+
+    def _export(self, fn) -> Dict[str, "torch.Tensor"]:
+        import torch
+        bufs = {}
+
+        def get(key):
+            key = self.TIED.get(key, key) if self.TIED.get(key, key) in self._shapes else key
+            if key not in bufs:
+                bufs[key] = torch.zeros(self._shapes[key], dtype=torch.float32, device=self._dev)
+            return bufs[key]
+
+        w, keep = weights_struct(get, self.cfg["num_layers"], self._keys)
+        torch.cuda.synchronize(self._dev)
+        check(fn(self._h, ctypes.byref(w)))
+        torch.cuda.synchronize(self._dev)
+        out = {}
+        for k in self._keys:
+            if k in self._passthrough:
+                out[k] = self._passthrough[k]
+            else:
+                src = self.TIED.get(k, k)
+                out[k] = bufs[src if src in bufs else k].cpu()
+        for k, src in self.TIED.items():       # tied entries share storage, as in model.state_dict()
+            if k in out and src in out:
+                out[k] = out[src]
+        del keep
+        return out
+
+    def state_dict(self) -> Dict[str, "torch.Tensor"]:
+        """fp32 CPU tensors under the keys of the state_dict given at construction (model.state_dict(),
+        MLM_PLL/main.py:155)."""
+        return self._export(self._lib.pllb_train_export)
+
+    def grads(self) -> Dict[str, "torch.Tensor"]:
+        """Gradients of the last mode-1 / mode-2 step, same keys (parity tests)."""
+        return self._export(self._lib.pllb_train_export_grads)
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.pllb_train_kernel_launches(self._h))
 
 
 # ---------------------------------------------------------------------- stage 4

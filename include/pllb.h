@@ -236,6 +236,55 @@ int pllb_rescore_scores(const double* am, const double* lm, const int64_t* len,
                         int32_t N, int32_t n_best, double weight, int32_t variant,
                         double* out_scores, void* stream);
 
+/* ---- MLM fine-tuning: replaces the train_mode=True branch of run_one_epoch
+ * (MLM_PLL/main.py:73-99: BertForMaskedLM.forward with labels, loss.backward(),
+ * torch.optim.AdamW.step(), zero_grad) and its loss-only twin (train_mode=False,
+ * do_scoring=False — the dev pass of mlm_finetune_bert, MLM_PLL/main.py:146-153).
+ * A batch is what collate (MLM_PLL/main.py:28-54) builds: B sequences zero-padded to T
+ * positions; the loss is CrossEntropyLoss() over ALL B*T positions (labels are the whole
+ * unmasked sequence, pad positions carry label 0 = [PAD]; nothing is ignored).
+ * fp32 master weights / gradients / Adam moments; bf16 operands, fp32 accumulation in
+ * every GEMM (forward, dgrad, wgrad).  The decoder weight is tied to the word embeddings
+ * and the decoder bias is cls.predictions.bias. */
+typedef struct pllb_train_desc {
+  float lr;                 /* config.lr (MLM_PLL/config/train.yaml:5: 1e-5)          */
+  float beta1, beta2;       /* torch.optim.AdamW defaults 0.9, 0.999                  */
+  float adam_eps;           /* 1e-8                                                    */
+  float weight_decay;       /* 0.01, applied to EVERY parameter (model.parameters())  */
+  float hidden_dropout;     /* BertConfig.hidden_dropout_prob (0.1); 0 for parity runs */
+  float attention_dropout;  /* BertConfig.attention_probs_dropout_prob (0.1)          */
+  uint64_t seed;            /* dropout stream (the masks are a stateless hash)        */
+  int32_t pad_id;           /* BertConfig.pad_token_id (0): the embedding lookup sends
+                               no gradient to this row (nn.Embedding padding_idx)     */
+  int32_t max_rows;         /* capacity: B * T of the largest batch                    */
+  int32_t max_seq;          /* capacity: largest T (<= max_position, <= 512)           */
+} pllb_train_desc;
+
+typedef struct pllb_trainer_ctx* pllb_trainer;
+
+/* weights: DEVICE fp32 state_dict tensors (copied; the MLM head is required). */
+int pllb_train_create(pllb_trainer* out, const pllb_model_desc* desc, const pllb_weights* weights,
+                      const pllb_train_desc* train, int device);
+int pllb_train_destroy(pllb_trainer t);
+int64_t pllb_train_workspace_bytes(pllb_trainer t);
+int64_t pllb_train_kernel_launches(pllb_trainer t);
+/* A fresh optimizer: zero moments, step count 0, learning rate lr — the reference
+ * re-creates AdamW at the start of every epoch (MLM_PLL/main.py:76). */
+int pllb_train_reset_optimizer(pllb_trainer t, float lr);
+/* One batch, HOST buffers.  input_ids, labels: int32[B*T] row-major (zero-padded as collate
+ * does); n_valid: int32[B], the number of leading positions with attention_mask 1.
+ * mode 0: loss only (model.eval(): no dropout, no update);
+ * mode 1: forward (dropout active) + backward + AdamW step;
+ * mode 2: forward + backward, no update (gradients stay readable: parity tests).
+ * out_loss: the batch loss (output.loss.item(), MLM_PLL/main.py:109).  Synchronises. */
+int pllb_train_step_host(pllb_trainer t, const int32_t* input_ids, const int32_t* n_valid,
+                         const int32_t* labels, int32_t B, int32_t T, int32_t mode, float* out_loss);
+/* Writes the fp32 master weights (model.state_dict(), MLM_PLL/main.py:155) / the gradients of
+ * the last mode-1/2 step into the caller's DEVICE tensors; a NULL pointer skips that tensor;
+ * q/k/v are un-stacked; decoder_w is written only if it is not the word_emb pointer. */
+int pllb_train_export(pllb_trainer t, const pllb_weights* dst);
+int pllb_train_export_grads(pllb_trainer t, const pllb_weights* dst);
+
 #ifdef __cplusplus
 }
 #endif

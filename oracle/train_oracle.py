@@ -77,7 +77,7 @@ def loss_and_grads(sd, cfg, rows: List[dict]):
     ids, am, lab, *_ = pll_oracle.collate(rows)
     loss = batch_loss(params, cfg, ids, am, lab)
     loss.backward()
-    return float(loss), {k: p.grad.detach().clone() for k, p in params.items()}
+    return loss.item(), {k: p.grad.detach().clone() for k, p in params.items()}
 
 
 def run_one_epoch(params, cfg, rows: List[dict], batch_size: int, lr: float, train_mode: bool,

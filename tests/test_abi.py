@@ -33,6 +33,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.LayerWeights) == 16 * 8
     assert ctypes.sizeof(_lib.Weights) == 12 * 8
     assert ctypes.sizeof(_lib.Stats) == 8 * 5 + 8 + 4 + 4 + 8
+    assert ctypes.sizeof(_lib.TrainDesc) == 56 and _lib.TrainDesc.seed.offset == 32 and _lib.TrainDesc.max_seq.offset == 48
 
 
 def test_product_package_never_imports_the_oracle():
@@ -54,3 +55,5 @@ def test_compute_calls_fail_loudly_without_gpu():
     from asr_rescoring_b200 import synth
     with pytest.raises(_lib.PllbError):
         engine.PllScorer(synth.random_init_state_dict(synth.BERT_TINY, 1), synth.BERT_TINY)
+    with pytest.raises(_lib.PllbError):
+        engine.MlmTrainer(synth.random_init_state_dict(synth.BERT_TINY, 1), synth.BERT_TINY)

@@ -109,8 +109,10 @@ def test_drop_in_function_surface():
     assert m.skeleton_from_rows(rows) == {"u": {"hyp_1": 0, "hyp_2": 0}, "v": {"hyp_1": 0}}
     with pytest.raises(KeyError):            # quirk 3: no hyp_1 row for an utterance
         m.skeleton_from_rows([{"utt_id": "w", "hyp_id": "hyp_2"}])
-    with pytest.raises(NotImplementedError):
-        m.run_one_epoch(None, None, [], {}, train_mode=True)
+    with pytest.raises(NotImplementedError):      # train_mode + do_scoring: never used by the reference's drivers
+        m.run_one_epoch(None, None, [], {}, train_mode=True, do_scoring=True)
+    with pytest.raises(TypeError):                # the loss / training pass needs a trainer, not a scorer
+        m.run_one_epoch(None, object(), [], None, train_mode=True, do_scoring=False)
 
 
 def test_preprocess_rows_match_reference_schema():
@@ -353,6 +355,8 @@ def test_preprocess_main_writes_the_three_packed_splits(tmp_path):
         d.mkdir(parents=True)
         texts[split] = {f"{split}_u{i}": {"hyp_1": "你好嗎", "hyp_2": "", "hyp_3": "好"} for i in range(3)}
         (d / "hyps_text.json").write_text(json.dumps(texts[split], ensure_ascii=False), encoding="utf-8")
+        (d / "ref_text.json").write_text(json.dumps({f"{split}_u{i}": "你好" for i in range(2)}, ensure_ascii=False),
+                                         encoding="utf-8")
     script = os.path.join(ROOT, "asr-rescoring_b200", "MLM_PLL", "preprocess.py")
     env = {k: v for k, v in os.environ.items() if k != "PLLB_VOCAB"}
     out = subprocess.run([sys.executable, script], cwd=tmp_path / "MLM_PLL", env=env, capture_output=True, text=True)
@@ -365,3 +369,34 @@ def test_preprocess_main_writes_the_three_packed_splits(tmp_path):
         assert p["format"] == "pllb-packed-v1" and p["tokenizer"] == "synthetic"
         assert p["utt_id"] == [u for u in texts[split] for _ in range(3)] and p["hyp_id"] == ["hyp_1", "hyp_2", "hyp_3"] * 3
         assert p["offsets"] == [0, 3, 3, 4, 7, 7, 8, 11, 11, 12] and p["tokens"][:3] == tk.encode("你好嗎")
+    from oracle import pll_oracle
+    for split in ("train", "dev"):                    # the two for_training jobs: the reference's row list
+        rows = json.load(open(tmp_path / "MLM_PLL" / "preprocessed_data" / "for_training" / f"{split}.json", encoding="utf-8"))
+        exp = [r for i in range(2) for r in pll_oracle.expand_rows(tk.encode("你好"), f"{split}_u{i}", None)]
+        assert rows == exp
+
+
+def test_training_batches_match_collate_and_dataloader_order():
+    from types import SimpleNamespace
+    """pad_batch == the reference's collate (MLM_PLL/main.py:28-54, via the oracle restatement);
+    RowLoader(shuffle=True) yields the order torch's DataLoader yields under the same global seed
+    (MLM_PLL/main.py:57-70 with config.shuffle)."""
+    import importlib
+    import torch
+    from torch.utils.data import DataLoader
+    from oracle import pll_oracle, train_oracle
+    m = importlib.import_module("asr_rescoring_b200.MLM_PLL.main")
+    rows = train_oracle.training_rows([[200, 201, 202], [300], [400, 401, 402, 403, 404], [500, 501]])
+    ids, am, lab = m.pad_batch(rows[:7])
+    o_ids, o_am, o_lab, *_ = pll_oracle.collate(rows[:7])
+    assert np.array_equal(ids, o_ids.numpy()) and np.array_equal(am, o_am.numpy()) and np.array_equal(lab, o_lab.numpy())
+    conf = SimpleNamespace(shuffle=True, batch_size=3, num_worker=0)
+    torch.manual_seed(10)
+    mine = [[r["input_ids"] for r in b] for b in m.set_dataloader(conf, m.MyDataset(rows), False)]
+    mine += [[r["input_ids"] for r in b] for b in m.set_dataloader(conf, m.MyDataset(rows), False)]    # a second epoch
+    torch.manual_seed(10)
+    dl = DataLoader(dataset=m.MyDataset(rows), collate_fn=lambda b: b, batch_size=3, num_workers=0, shuffle=True)
+    ref = [[r["input_ids"] for r in b] for b in dl] + [[r["input_ids"] for r in b] for b in dl]
+    assert mine == ref and len(mine) == 2 * ((len(rows) + 2) // 3)
+    seq = [[r["input_ids"] for r in b] for b in m.set_dataloader(conf, m.MyDataset(rows), True)]        # for_scoring: no shuffle
+    assert [x for b in seq for x in b] == [r["input_ids"] for r in rows]

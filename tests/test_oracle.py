@@ -133,3 +133,46 @@ def test_algorithmic_flops_formula():
     # bert-base-chinese, L=14 -> 38.65 GFLOP per hypothesis
     f = pll_oracle.algorithmic_flops([14], synth.BERT_BASE_CHINESE)
     assert abs(f / 1e9 - 38.65) < 0.05
+
+
+# ---------------------------------------------------------------------- MLM fine-tuning oracle
+def _summary(t):
+    import torch
+    v = t.detach().double().reshape(-1)
+    g = torch.Generator().manual_seed(1234 + v.numel() % 977)
+    sign = torch.randint(0, 2, (v.numel(),), generator=g, dtype=torch.int64).double() * 2 - 1
+    return float(v.norm()), float((v * sign).sum())
+
+
+def test_training_oracle_matches_the_reference_training_golden(gold_dir):
+    """oracle/train_oracle.py (autograd restatement of run_one_epoch(train_mode=True)) against
+    tests/golden/train_golden.json, which oracle/make_golden_train.py recorded from the UNMODIFIED
+    MLM_PLL/main.py loop on transformers.BertForMaskedLM (dropout 0): first-batch loss and per-tensor
+    gradient summaries, the epoch losses of train and dev passes, the final weights."""
+    from oracle import train_oracle
+    gold = json.load(open(os.path.join(gold_dir, "train_golden.json")))
+    for case in gold["cases"]:
+        cfg, bs, lr = case["cfg"], case["batch_size"], case["lr"]
+        sd = synth.random_init_state_dict(cfg, case["seed"], case["perturb"])
+        train_rows = train_oracle.training_rows(case["train_tokens"])
+        dev_rows = train_oracle.training_rows(case["dev_tokens"])
+        loss, grads = train_oracle.loss_and_grads(sd, cfg, train_rows[:bs])
+        assert abs(loss - case["first_batch_loss"]) < 1e-5
+        for k, ref in case["first_batch_grads"].items():
+            name = train_oracle.TIED.get(k, k)
+            norm, proj = _summary(grads[name])
+            assert abs(norm - ref["norm"]) <= 2e-4 * ref["norm"] + 1e-7, (k, norm, ref["norm"])
+            assert abs(proj - ref["proj"]) <= 2e-4 * ref["norm"] + 1e-7, (k, proj, ref["proj"])
+        if case["name"] != "tiny_lr1e-5":          # one full case is enough for the CPU budget
+            continue
+        params = train_oracle.parameters(sd)
+        for e in range(case["epochs"]):
+            tr = train_oracle.run_one_epoch(params, cfg, train_rows, bs, lr, True)
+            dv = train_oracle.run_one_epoch(params, cfg, dev_rows, bs, lr, False)
+            assert abs(tr - case["train_loss"][e]) < 2e-4 and abs(dv - case["dev_loss"][e]) < 2e-4
+        final = train_oracle.state_dict_of(params)
+        for k, ref in case["final_minus_init"].items():
+            if k.endswith("attention.self.key.bias"):
+                continue        # its true gradient is 0 (softmax ignores a per-row constant): Adam amplifies pure rounding noise
+            norm, proj = _summary(final[k] - sd[k])
+            assert abs(norm - ref["norm"]) <= 0.02 * ref["norm"] + 1e-9, (k, norm, ref["norm"])
