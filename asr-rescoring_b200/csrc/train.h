@@ -33,7 +33,9 @@ int launch_train_attn_fwd(const void* qkv, const int32_t* n_valid, int R, int T,
                           void* ctx, float* lse, cudaStream_t s);
 int launch_train_attn_bwd(const void* qkv, const float* dctx, const float* lse, const int32_t* n_valid, int R, int T, int H,
                           int NH, TrainDrop drop, uint32_t site, float* dqkv, float* Dscratch, cudaStream_t s);
-// per-row cross entropy over V of the Vp logit columns, mean loss, dlogits = (softmax - onehot) / R (bf16, may be null)
+int launch_train_scale(float* x, int64_t n, float alpha, cudaStream_t s);
+// per-row cross entropy over V of the Vp logit columns, mean loss, dlogits = softmax - onehot (bf16, may be null;
+// the 1/R of the mean is applied by the caller in fp32)
 int launch_train_ce(const float* logits, const int32_t* labels, int R, int V, int Vp, float* loss_rows, void* dlogits,
                     float* out_loss, cudaStream_t s);
 int launch_train_embed_bwd(const float* dz, const int32_t* ids, int B, int T, int H, int max_pos, int pad_id, float* dword,

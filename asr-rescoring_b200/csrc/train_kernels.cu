@@ -373,9 +373,12 @@ attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restric
 }
 
 // ---------------------------------------------------------------- cross entropy over every position
-// loss_r = logsumexp(logits[r, :V]) - logits[r, label_r];  dlogits = (softmax - onehot) * scale (bf16)
+// loss_r = logsumexp(logits[r, :V]) - logits[r, label_r];  dlogits = softmax - onehot (bf16, UNSCALED: the
+// -1 of the label column stays exact; with the 1/R of the mean folded in, every one-hot entry would
+// carry the same bf16 rounding error of 1/R — a systematic scale error of up to 0.4 % on every
+// gradient.  The consumers multiply by 1/R in fp32.)
 __global__ void __launch_bounds__(256)
-ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int V, int Vp, float scale,
+ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int V, int Vp,
           float* __restrict__ loss_rows, __nv_bfloat16* __restrict__ dlogits) {
   __shared__ float red[8];
   __shared__ float bc;
@@ -404,10 +407,14 @@ ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, 
     __nv_bfloat16* d = dlogits + (size_t)r * Vp;
     for (int c = tid; c < Vp; c += 256) {
       float g = 0.f;
-      if (c < V) g = (__expf(x[c] - lse) - (c == label ? 1.f : 0.f)) * scale;
+      if (c < V) g = __expf(x[c] - lse) - (c == label ? 1.f : 0.f);
       d[c] = __float2bfloat16_rn(g);
     }
   }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, int64_t n, float alpha) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= alpha;
 }
 
 // mean of the R per-row losses in a fixed order (double accumulation); single block
@@ -585,10 +592,17 @@ int launch_train_attn_bwd(const void* qkv, const float* dctx, const float* lse, 
 int launch_train_ce(const float* logits, const int32_t* labels, int R, int V, int Vp, float* loss_rows, void* dlogits,
                     float* out_loss, cudaStream_t s) {
   if (R <= 0) return PLLB_OK;
-  ce_kernel<<<R, 256, 0, s>>>(logits, labels, V, Vp, 1.f / (float)R, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits));
+  ce_kernel<<<R, 256, 0, s>>>(logits, labels, V, Vp, loss_rows, reinterpret_cast<__nv_bfloat16*>(dlogits));
   PLLB_LAUNCH_CHECK("ce_kernel");
   loss_mean_kernel<<<1, 256, 0, s>>>(loss_rows, R, out_loss);
   PLLB_LAUNCH_CHECK("loss_mean_kernel");
+  return PLLB_OK;
+}
+
+int launch_train_scale(float* x, int64_t n, float alpha, cudaStream_t s) {
+  if (n <= 0) return PLLB_OK;
+  scale_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, n, alpha);
+  PLLB_LAUNCH_CHECK("scale_kernel");
   return PLLB_OK;
 }
 

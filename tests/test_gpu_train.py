@@ -72,6 +72,31 @@ def test_batch_loss_and_gradients_vs_oracle(gold_dir):
     assert float(g["bert.embeddings.word_embeddings.weight"][0].abs().sum()) > 0
 
 
+def test_bert_base_shape_two_layers_vs_oracle():
+    """H = 768 / 12 heads / I = 3072 / vocab 21128 (not a multiple of the 256-column vocab tile): the shape
+    the reference fine-tunes (train.yaml:23-24), two layers deep so the CPU oracle stays cheap."""
+    cfg = dict(synth.BERT_BASE_CHINESE, num_layers=2)
+    sd = synth.random_init_state_dict(cfg, 10, perturb=True)
+    nb = synth.make_nbest(5, 1, seed=7)
+    tok, off = nb.packed_tokens()
+    rows = train_oracle.training_rows([[int(t) for t in tok[off[i]:off[i + 1]]] for i in range(len(off) - 1)])[5:37]
+    ids, am, lab = _batch(rows)
+    o_loss, o_grads = train_oracle.loss_and_grads(sd, cfg, rows)
+    with engine.MlmTrainer(sd, cfg, hidden_dropout=0.0, attention_dropout=0.0, max_rows=ids.size, max_seq=ids.shape[1]) as tr:
+        loss = tr.step(ids, am, lab, mode=2)
+        g = tr.grads()
+    assert abs(loss - o_loss) <= 0.02, (loss, o_loss)
+    worst = 0.0
+    for k, og in o_grads.items():
+        if k.endswith(KEY_BIAS):
+            continue
+        d, og = g[k].double(), og.double()
+        rel = float((d - og).norm() / (og.norm() + 1e-30))
+        worst = max(worst, rel)
+        assert rel <= 0.06, (k, rel)
+    print(f"bert-base shape, 2 layers: loss {loss:.5f} (oracle {o_loss:.5f}), worst gradient rel L2 error {worst:.4f}")
+
+
 def test_adamw_update_matches_torch_given_the_same_gradients(gold_dir):
     """The optimizer in isolation: gradients of a mode-2 pass, then a mode-1 pass on the same batch
     (same gradients: no dropout, deterministic kernels); torch.optim.AdamW on CPU fed with the
