@@ -21,9 +21,11 @@ int launch_train_ln_fwd(const float* y, const float* res, const float* g, const 
 // dy <- (dy + add) [* dropout mask site_in]; dz = LayerNorm backward; dz_drop = dz [* dropout mask site_out]
 int launch_train_ln_bwd(float* dy, const float* add, const float* g, const float* xhat, const float* rstd, int R, int H,
                         TrainDrop drop, int site_in, int site_out, float* dz, float* dz_drop, cudaStream_t s);
-// out_sum[c] = sum_r dy[r,c]; out_dot[c] = sum_r dy[r,c] * xhat[r,c] (either may be null)
+// out_sum[c] = sum_r dy[r,c]; out_dot[c] = sum_r dy[r,c] * xhat[r,c] (either may be null).
+// scratch: 2 * TRAIN_COLSUM_SPLITS * C floats for the row-sliced form (nullptr: one slice)
+constexpr int TRAIN_COLSUM_SPLITS = 64;
 int launch_train_colsum(const void* dy, bool dy_bf16, const float* xhat, int R, int C, float* out_sum, float* out_dot,
-                        cudaStream_t s);
+                        float* scratch, cudaStream_t s);
 int launch_train_gelu_fwd(const float* f, int64_t n, void* out16, float* out32, cudaStream_t s);
 int launch_train_gelu_bwd(float* dg, const float* f, int64_t n, cudaStream_t s);
 // src [R, C] (fp32 or bf16) -> dst16 [R, C] and / or dstT [C, Rp] (bf16; transposed columns >= R zero)
@@ -39,7 +41,7 @@ int launch_train_scale(float* x, int64_t n, float alpha, cudaStream_t s);
 int launch_train_ce(const float* logits, const int32_t* labels, int R, int V, int Vp, float* loss_rows, void* dlogits,
                     float* out_loss, cudaStream_t s);
 int launch_train_embed_bwd(const float* dz, const int32_t* ids, int B, int T, int H, int max_pos, int pad_id, float* dword,
-                           float* dpos, float* dtype0, cudaStream_t s);
+                           float* dpos, float* dtype0, float* scratch, cudaStream_t s);
 int launch_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                        float wd, int64_t step, cudaStream_t s);
 

@@ -61,7 +61,8 @@ struct pllb_trainer_ctx {
   __nv_bfloat16 *xlast16 = nullptr, *tn16 = nullptr, *dlogits16 = nullptr;
   float *logits = nullptr, *loss_rows = nullptr, *loss_dev = nullptr;
   // scratch
-  float *h32 = nullptr, *y32 = nullptr, *dh32 = nullptr, *dz32 = nullptr, *dzd32 = nullptr, *Dq = nullptr, *zeros = nullptr;
+  float *h32 = nullptr, *y32 = nullptr, *dh32 = nullptr, *dz32 = nullptr, *dzd32 = nullptr, *Dq = nullptr, *zeros = nullptr,
+        *colsum_scratch = nullptr;
   __nv_bfloat16 *d16 = nullptr, *dT16 = nullptr, *xT16 = nullptr;
   int64_t step = 0;        // optimizer steps since the last reset (Adam bias correction)
   int64_t calls = 0;       // forward passes since create (dropout stream)
@@ -127,7 +128,7 @@ int linear_bwd(pllb_trainer_ctx* c, const float* dy32, const __nv_bfloat16* x16,
                Span w, Span b, float* dx32, cudaStream_t s) {
   const int Rp = (int)round_up(R, 64);
   RC(launch_train_cast_transpose(dy32, false, R, N, Rp, c->d16, c->dT16, s));
-  RC(launch_train_colsum(dy32, false, nullptr, R, N, c->G + b.off, nullptr, s));
+  RC(launch_train_colsum(dy32, false, nullptr, R, N, c->G + b.off, nullptr, c->colsum_scratch, s));
   RC(launch_train_cast_transpose(x16, true, R, K, Rp, nullptr, c->xT16, s));
   RC(gemm(c->dT16, c->xT16, c->zeros, c->G + w.off, N, K, Rp, EPI_BIAS_F32, s));            // dW [N, K]
   if (dx32) RC(gemm(c->d16, wT16, c->zeros, dx32, R, K, N, EPI_BIAS_F32, s));                // dX [R, K]
@@ -239,7 +240,7 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
     // ---------------- backward: head
     RC(launch_train_cast_transpose(c->dlogits16, true, R, Vp, Rp, nullptr, c->dT16, s));
     const float inv_r = 1.f / (float)R;        // the mean over the B*T positions, applied in fp32 (ce_kernel)
-    RC(launch_train_colsum(c->dlogits16, true, nullptr, R, Vp, G + c->dec_b.off, nullptr, s));
+    RC(launch_train_colsum(c->dlogits16, true, nullptr, R, Vp, G + c->dec_b.off, nullptr, c->colsum_scratch, s));
     RC(launch_train_scale(G + c->dec_b.off, Vp, inv_r, s));
     RC(launch_train_cast_transpose(c->tn16, true, R, H, Rp, nullptr, c->xT16, s));
     RC(gemm(c->dT16, c->xT16, c->zeros, G + c->word.off, Vp, H, Rp, EPI_BIAS_F32, s));       // decoder part of dE
@@ -247,7 +248,7 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
     RC(gemm(c->dlogits16, c->ET16, c->zeros, c->dh32, R, H, Vp, EPI_BIAS_F32, s));           // d(transform LayerNorm output)
     RC(launch_train_scale(c->dh32, (int64_t)R * H, inv_r, s));
     RC(launch_train_ln_bwd(c->dh32, nullptr, P + c->head_g.off, c->xhat_h, c->rstd_h, R, H, none, -1, -1, c->dz32, nullptr, s));
-    RC(launch_train_colsum(c->dh32, false, c->xhat_h, R, H, G + c->head_be.off, G + c->head_g.off, s));
+    RC(launch_train_colsum(c->dh32, false, c->xhat_h, R, H, G + c->head_be.off, G + c->head_g.off, c->colsum_scratch, s));
     RC(launch_train_gelu_bwd(c->dz32, c->t_f32, (int64_t)R * H, s));
     RC(linear_bwd(c, c->dz32, c->xlast16, c->headT16, R, H, H, c->head_w, c->head_b, c->dh32, s));
     // ---------------- backward: encoder layers.  dh32 = gradient of the layer output through the
@@ -259,14 +260,14 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
       // BertOutput: LN(dropout(FFN2(g)) + h1)
       RC(launch_train_ln_bwd(c->dh32, have_res ? c->dz32 : nullptr, P + t.out_g.off, t.xhat2, t.rstd2, R, H, hd, -1,
                              dr ? (int)(SITE_FF2 + 8 * l) : -1, c->dz32, dr ? c->dzd32 : nullptr, s));
-      RC(launch_train_colsum(c->dh32, false, t.xhat2, R, H, G + t.out_be.off, G + t.out_g.off, s));
+      RC(launch_train_colsum(c->dh32, false, t.xhat2, R, H, G + t.out_be.off, G + t.out_g.off, c->colsum_scratch, s));
       RC(linear_bwd(c, dr ? c->dzd32 : c->dz32, t.g16, t.ff2T16, R, H, I, t.ff2_w, t.ff2_b, c->y32, s));   // y32 = dg [R, I]
       RC(launch_train_gelu_bwd(c->y32, t.f, (int64_t)R * I, s));
       RC(linear_bwd(c, c->y32, t.h1_16, t.ff1T16, R, I, H, t.ff1_w, t.ff1_b, c->dh32, s));                 // dh32 = dh1 via the FFN
       // BertSelfOutput: LN(dropout(AO(ctx)) + x)
       RC(launch_train_ln_bwd(c->dh32, c->dz32, P + t.ao_g.off, t.xhat1, t.rstd1, R, H, hd, -1,
                              dr ? (int)(SITE_AO + 8 * l) : -1, c->dz32, dr ? c->dzd32 : nullptr, s));
-      RC(launch_train_colsum(c->dh32, false, t.xhat1, R, H, G + t.ao_be.off, G + t.ao_g.off, s));
+      RC(launch_train_colsum(c->dh32, false, t.xhat1, R, H, G + t.ao_be.off, G + t.ao_g.off, c->colsum_scratch, s));
       RC(linear_bwd(c, dr ? c->dzd32 : c->dz32, t.ctx, t.aoT16, R, H, H, t.ao_w, t.ao_b, c->dh32, s));     // dh32 = dctx
       RC(launch_train_attn_bwd(t.qkv, c->dh32, t.lse, c->n_valid, R, T, H, NH, ad, SITE_ATT + 8 * l, c->y32, c->Dq, s));
       RC(linear_bwd(c, c->y32, t.x16, t.qkvT16, R, 3 * H, H, t.qkv_w, t.qkv_b, c->dh32, s));               // dh32 = dx via QKV
@@ -275,9 +276,9 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
     // ---------------- backward: embeddings (dropout sits AFTER the LayerNorm here)
     RC(launch_train_ln_bwd(c->dh32, have_res ? c->dz32 : nullptr, P + c->emb_g.off, c->xhat_e, c->rstd_e, R, H, hd,
                            hd.thresh != 0 ? (int)SITE_EMB : -1, -1, c->dz32, nullptr, s));
-    RC(launch_train_colsum(c->dh32, false, c->xhat_e, R, H, G + c->emb_b.off, G + c->emb_g.off, s));
+    RC(launch_train_colsum(c->dh32, false, c->xhat_e, R, H, G + c->emb_b.off, G + c->emb_g.off, c->colsum_scratch, s));
     RC(launch_train_embed_bwd(c->dz32, c->ids, B, T, H, d.max_position, c->t.pad_id, G + c->word.off, G + c->pos.off,
-                              G + c->type.off, s));
+                              G + c->type.off, c->colsum_scratch, s));
     if (mode == 1) {
       c->step += 1;
       RC(launch_train_adamw(c->P, c->G, c->M, c->V, c->n_flat, c->t.lr, c->t.beta1, c->t.beta2, c->t.adam_eps,
@@ -393,6 +394,7 @@ int pllb_train_create(pllb_trainer* out, const pllb_model_desc* desc, const pllb
   TRY(talloc(c, &c->h32, R * H)); TRY(talloc(c, &c->y32, R * wide)); TRY(talloc(c, &c->dh32, R * H));
   TRY(talloc(c, &c->dz32, R * H)); TRY(talloc(c, &c->dzd32, R * H)); TRY(talloc(c, &c->Dq, R * NH));
   TRY(talloc(c, &c->zeros, std::max(Vp, wide), true));
+  TRY(talloc(c, &c->colsum_scratch, (int64_t)2 * TRAIN_COLSUM_SPLITS * std::max(Vp, wide)));
   TRY(talloc(c, &c->d16, R * std::max(wide, H))); TRY(talloc(c, &c->dT16, (int64_t)std::max(wide, Vp) * Rp));
   TRY(talloc(c, &c->xT16, (int64_t)std::max(I, H) * Rp));
   if (cudaHostAlloc(&c->host_stage, sizeof(int32_t) * (size_t)(3 * R), cudaHostAllocDefault) != cudaSuccess) {
