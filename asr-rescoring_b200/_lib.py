@@ -83,6 +83,7 @@ SIGNATURES = {
     "pllb_train_destroy": (c_int, [c_void_p]),
     "pllb_train_workspace_bytes": (c_int64, [c_void_p]),
     "pllb_train_kernel_launches": (c_int64, [c_void_p]),
+    "pllb_train_graph_replays": (c_int64, [c_void_p]),
     "pllb_train_reset_optimizer": (c_int, [c_void_p, c_float]),
     "pllb_train_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_float)]),
     "pllb_train_export": (c_int, [c_void_p, POINTER(Weights)]),

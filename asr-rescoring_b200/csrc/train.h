@@ -5,8 +5,16 @@
 
 namespace pllb {
 
+// Scalars that change from step to step live in DEVICE memory (written before every step), not in
+// kernel arguments, so a captured CUDA graph of the step can be replayed unchanged.
+struct TrainStepParams {
+  uint64_t seed;          // dropout: run seed mixed with the forward-pass number
+  float adam_step_size;   // lr / (1 - beta1^t)
+  float adam_bc2_sqrt;    // sqrt(1 - beta2^t)
+};
+
 struct TrainDrop {        // stateless dropout (train_kernels.cu: drop_factor)
-  uint64_t seed;          // run seed mixed with the step number
+  const uint64_t* seed;   // DEVICE pointer (TrainStepParams.seed)
   uint32_t thresh;        // drop iff hash < thresh; 0 = no dropout
   float inv_keep;         // 1 / (1 - p)
 };
@@ -42,7 +50,8 @@ int launch_train_ce(const float* logits, const int32_t* labels, int R, int V, in
                     float* out_loss, cudaStream_t s);
 int launch_train_embed_bwd(const float* dz, const int32_t* ids, int B, int T, int H, int max_pos, int pad_id, float* dword,
                            float* dpos, float* dtype0, float* scratch, cudaStream_t s);
+// scalars: DEVICE TrainStepParams (adam_step_size, adam_bc2_sqrt of this step)
 int launch_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                       float wd, int64_t step, cudaStream_t s);
+                       float wd, const TrainStepParams* scalars, cudaStream_t s);
 
 }  // namespace pllb

@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
 #include "common.h"
@@ -67,6 +69,17 @@ struct pllb_trainer_ctx {
   int64_t step = 0;        // optimizer steps since the last reset (Adam bias correction)
   int64_t calls = 0;       // forward passes since create (dropout stream)
   int64_t launches = 0;
+  // per-step scalars (device copy read by the kernels; pinned host copy filled before every step)
+  TrainStepParams* params_dev = nullptr;
+  TrainStepParams* params_host = nullptr;
+  // CUDA graphs of the step, one per (B, T, mode): the step is ~575 small launches (launch-bound at the
+  // reference's batch size), all with shape-static arguments.  A shape runs eagerly the first time
+  // (shared-memory opt-ins, tensor-map cache), is captured the second time and replayed from then on.
+  cudaStream_t stream = nullptr;     // every step runs here (stream capture is not possible on the legacy stream)
+  bool use_graph = true;   // PLLB_TRAIN_GRAPH=0 disables
+  struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  int64_t graph_replays = 0;
 };
 
 namespace {
@@ -188,7 +201,7 @@ int export_flat(pllb_trainer_ctx* c, const float* buf, const pllb_weights* w) {
 
 TrainDrop make_drop(const pllb_trainer_ctx* c, float p, bool train) {
   TrainDrop d{};
-  d.seed = c->t.seed * 0x9E3779B97F4A7C15ull + (uint64_t)c->calls * 0xC2B2AE3D27D4EB4Full;
+  d.seed = &c->params_dev->seed;
   if (train && p > 0.f) {
     d.thresh = (uint32_t)std::min<double>(4294967295.0, (double)p * 4294967296.0);
     d.inv_keep = 1.f / (1.f - p);
@@ -199,14 +212,13 @@ TrainDrop make_drop(const pllb_trainer_ctx* c, float p, bool train) {
   return d;
 }
 
+// Every launch of one step (shape-static arguments only; the per-step scalars are read from params_dev).
 // mode 0: loss only (model.eval()); 1: forward + backward + AdamW step; 2: forward + backward, no update
-int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host, cudaStream_t s) {
+int enqueue_step(pllb_trainer_ctx* c, int B, int T, int mode, cudaStream_t s) {
   const pllb_model_desc& d = c->d;
   const int H = d.hidden, I = d.intermediate, NH = d.num_heads, NL = d.num_layers, Vp = c->Vp, V = d.vocab;
   const int R = B * T, Rp = (int)round_up(R, 64);
   const bool train = mode != 0;
-  const int64_t launches_before = g_launch_counter;
-  c->calls += 1;
   const TrainDrop hd = make_drop(c, c->t.hidden_dropout, train), ad = make_drop(c, c->t.attention_dropout, train);
   float* P = c->P;
   // ---------------- forward
@@ -230,7 +242,7 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
   // MLM head on EVERY row (labels are the whole sequence, MLM_PLL/preprocess.py:24-28)
   RC(gemm(c->xlast16, c->head16, P + c->head_b.off, c->t_f32, R, H, H, EPI_BIAS_F32, s));
   RC(launch_train_gelu_fwd(c->t_f32, (int64_t)R * H, nullptr, c->y32, s));
-  TrainDrop none{0, 0, 1.f};
+  TrainDrop none{&c->params_dev->seed, 0, 1.f};
   RC(launch_train_ln_fwd(c->y32, nullptr, P + c->head_g.off, P + c->head_be.off, d.ln_eps, R, H, none, 0, nullptr, c->tn16,
                          c->xhat_h, c->rstd_h, s));
   RC(gemm(c->tn16, c->E16, P + c->dec_b.off, c->logits, R, Vp, H, EPI_BIAS_F32, s));
@@ -280,17 +292,57 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
     RC(launch_train_embed_bwd(c->dz32, c->ids, B, T, H, d.max_position, c->t.pad_id, G + c->word.off, G + c->pos.off,
                               G + c->type.off, c->colsum_scratch, s));
     if (mode == 1) {
-      c->step += 1;
       RC(launch_train_adamw(c->P, c->G, c->M, c->V, c->n_flat, c->t.lr, c->t.beta1, c->t.beta2, c->t.adam_eps,
-                            c->t.weight_decay, c->step, s));
+                            c->t.weight_decay, c->params_dev, s));
       RC(refresh_all(c, s));
     }
+  }
+  return PLLB_OK;
+}
+
+int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host, cudaStream_t s) {
+  // per-step scalars -> device (the previous step ended with a stream synchronise, so the pinned copy is free)
+  c->calls += 1;
+  if (mode == 1) c->step += 1;
+  const int64_t t = std::max<int64_t>(c->step, 1);
+  const double bc1 = 1.0 - std::pow((double)c->t.beta1, (double)t), bc2 = 1.0 - std::pow((double)c->t.beta2, (double)t);
+  c->params_host->seed = c->t.seed * 0x9E3779B97F4A7C15ull + (uint64_t)c->calls * 0xC2B2AE3D27D4EB4Full;
+  c->params_host->adam_step_size = (float)((double)c->t.lr / bc1);
+  c->params_host->adam_bc2_sqrt = (float)std::sqrt(bc2);
+  PLLB_CUDA(cudaMemcpyAsync(c->params_dev, c->params_host, sizeof(TrainStepParams), cudaMemcpyHostToDevice, s));
+  const uint64_t key = ((uint64_t)(uint32_t)B << 34) | ((uint64_t)(uint32_t)T << 2) | (uint64_t)mode;
+  pllb_trainer_ctx::GraphEntry* ge = c->use_graph ? &c->graphs[key] : nullptr;
+  if (ge && ge->exec) {
+    PLLB_CUDA(cudaGraphLaunch(ge->exec, s));
+    c->launches += ge->launches;
+    c->graph_replays += 1;
+  } else if (ge && ge->seen >= 1) {
+    const int64_t before = g_launch_counter;
+    PLLB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_step(c, B, T, mode, s);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess || !g) return fail(PLLB_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) return fail(PLLB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei));
+    ge->exec = exec;
+    ge->launches = g_launch_counter - before;
+    PLLB_CUDA(cudaGraphLaunch(ge->exec, s));
+    c->launches += ge->launches;
+    c->graph_replays += 1;
+  } else {
+    const int64_t before = g_launch_counter;
+    RC(enqueue_step(c, B, T, mode, s));
+    c->launches += g_launch_counter - before;
+    if (ge) ge->seen += 1;
   }
   if (out_loss_host) {
     PLLB_CUDA(cudaMemcpyAsync(out_loss_host, c->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, s));
     PLLB_CUDA(cudaStreamSynchronize(s));
   }
-  c->launches += g_launch_counter - launches_before;
   return PLLB_OK;
 }
 
@@ -397,7 +449,15 @@ int pllb_train_create(pllb_trainer* out, const pllb_model_desc* desc, const pllb
   TRY(talloc(c, &c->colsum_scratch, (int64_t)2 * TRAIN_COLSUM_SPLITS * std::max(Vp, wide)));
   TRY(talloc(c, &c->d16, R * std::max(wide, H))); TRY(talloc(c, &c->dT16, (int64_t)std::max(wide, Vp) * Rp));
   TRY(talloc(c, &c->xT16, (int64_t)std::max(I, H) * Rp));
-  if (cudaHostAlloc(&c->host_stage, sizeof(int32_t) * (size_t)(3 * R), cudaHostAllocDefault) != cudaSuccess) {
+  TRY(talloc(c, &c->params_dev, 1, true));
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    pllb_train_destroy(c);
+    return fail(PLLB_ERR_CUDA, "pllb_train_create: cudaStreamCreate failed");
+  }
+  if (const char* e = getenv("PLLB_TRAIN_GRAPH")) c->use_graph = atoi(e) != 0;
+  if (cudaHostAlloc(&c->params_host, sizeof(TrainStepParams), cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc(&c->host_stage, sizeof(int32_t) * (size_t)(3 * R), cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     pllb_train_destroy(c);
     return fail(PLLB_ERR_OOM, "pllb_train_create: pinned staging buffer");
@@ -417,22 +477,27 @@ int pllb_train_destroy(pllb_trainer c) {
   if (!c) return PLLB_OK;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  for (auto& kv : c->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : c->owned) cudaFree(p);
+  if (c->stream) cudaStreamDestroy(c->stream);
   if (c->host_stage) cudaFreeHost(c->host_stage);
+  if (c->params_host) cudaFreeHost(c->params_host);
   delete c;
   return PLLB_OK;
 }
 
 int64_t pllb_train_workspace_bytes(pllb_trainer c) { return c ? c->owned_bytes : 0; }
 int64_t pllb_train_kernel_launches(pllb_trainer c) { return c ? c->launches : 0; }
+int64_t pllb_train_graph_replays(pllb_trainer c) { return c ? c->graph_replays : 0; }
 
 int pllb_train_reset_optimizer(pllb_trainer c, float lr) {
   if (!c) return fail(PLLB_ERR_INVALID, "null trainer");
   PLLB_CUDA(cudaSetDevice(c->device));
   c->t.lr = lr;
   c->step = 0;
-  PLLB_CUDA(cudaMemsetAsync(c->M, 0, sizeof(float) * (size_t)c->n_flat, 0));
-  PLLB_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * (size_t)c->n_flat, 0));
+  PLLB_CUDA(cudaMemsetAsync(c->M, 0, sizeof(float) * (size_t)c->n_flat, c->stream));
+  PLLB_CUDA(cudaMemsetAsync(c->V, 0, sizeof(float) * (size_t)c->n_flat, c->stream));
   return PLLB_OK;
 }
 
@@ -456,7 +521,7 @@ int pllb_train_step_host(pllb_trainer c, const int32_t* input_ids, const int32_t
   for (int b = 0; b < B; ++b)
     if (n_valid[b] < 1 || n_valid[b] > T) return fail(PLLB_ERR_INVALID, "n_valid must be in [1, T]");
   PLLB_CUDA(cudaSetDevice(c->device));
-  cudaStream_t s = 0;
+  cudaStream_t s = c->stream;
   PLLB_CUDA(cudaStreamSynchronize(s));       // the pinned staging buffer of the previous call is free
   std::memcpy(c->host_stage, input_ids, sizeof(int32_t) * R);
   std::memcpy(c->host_stage + R, labels, sizeof(int32_t) * R);
@@ -473,12 +538,14 @@ int pllb_train_step_host(pllb_trainer c, const int32_t* input_ids, const int32_t
 int pllb_train_export(pllb_trainer c, const pllb_weights* dst) {
   if (!c || !dst || !dst->layers) return fail(PLLB_ERR_INVALID, "pllb_train_export: null argument");
   PLLB_CUDA(cudaSetDevice(c->device));
+  PLLB_CUDA(cudaStreamSynchronize(c->stream));
   return export_flat(c, c->P, dst);
 }
 
 int pllb_train_export_grads(pllb_trainer c, const pllb_weights* dst) {
   if (!c || !dst || !dst->layers) return fail(PLLB_ERR_INVALID, "pllb_train_export_grads: null argument");
   PLLB_CUDA(cudaSetDevice(c->device));
+  PLLB_CUDA(cudaStreamSynchronize(c->stream));
   return export_flat(c, c->G, dst);
 }
 

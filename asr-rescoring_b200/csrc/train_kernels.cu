@@ -38,7 +38,7 @@ __device__ __forceinline__ float wmax(float v) {
 // backward pass regenerates the same mask, nothing is stored.
 __device__ __forceinline__ float drop_factor(const TrainDrop& d, uint32_t site, uint64_t idx) {
   if (d.thresh == 0) return 1.f;
-  uint64_t x = d.seed + (uint64_t)site * 0x9E3779B97F4A7C15ull + idx * 0xD1B54A32D192ED03ull;
+  uint64_t x = __ldg(d.seed) + (uint64_t)site * 0x9E3779B97F4A7C15ull + idx * 0xD1B54A32D192ED03ull;
   x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
   x ^= x >> 27; x *= 0x94D049BB133111EBull;
   x ^= x >> 31;
@@ -494,8 +494,9 @@ word_grad_kernel(const float* __restrict__ dz, const int32_t* __restrict__ ids, 
 
 // ---------------------------------------------------------------- AdamW (torch.optim.AdamW, single-tensor path)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             int64_t n, float lr, float beta1, float beta2, float eps, float wd, float step_size,
-                             float bc2_sqrt) {
+                             int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+                             const TrainStepParams* __restrict__ scalars) {
+  const float step_size = scalars->adam_step_size, bc2_sqrt = scalars->adam_bc2_sqrt;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i] * (1.f - lr * wd);
     const float gi = g[i];
@@ -654,11 +655,9 @@ int launch_train_embed_bwd(const float* dz, const int32_t* ids, int B, int T, in
 }
 
 int launch_train_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                       float wd, int64_t step, cudaStream_t s) {
+                       float wd, const TrainStepParams* scalars, cudaStream_t s) {
   if (n <= 0) return PLLB_OK;
-  const double bc1 = 1.0 - std::pow((double)beta1, (double)step), bc2 = 1.0 - std::pow((double)beta2, (double)step);
-  adamw_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, (float)((double)lr / bc1),
-                                                (float)std::sqrt(bc2));
+  adamw_kernel<<<grid_for(n, 256), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, scalars);
   PLLB_LAUNCH_CHECK("adamw_kernel");
   return PLLB_OK;
 }

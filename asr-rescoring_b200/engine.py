@@ -363,6 +363,10 @@ class MlmTrainer:
     def kernel_launches(self) -> int:
         return int(self._lib.pllb_train_kernel_launches(self._h))
 
+    def graph_replays(self) -> int:
+        """Steps that ran as replays of a captured CUDA graph (PLLB_TRAIN_GRAPH=0 disables capture)."""
+        return int(self._lib.pllb_train_graph_replays(self._h))
+
 
 # ---------------------------------------------------------------------- stage 4
 def pack_strings(strings: Sequence[str]):

@@ -268,6 +268,9 @@ int pllb_train_create(pllb_trainer* out, const pllb_model_desc* desc, const pllb
 int pllb_train_destroy(pllb_trainer t);
 int64_t pllb_train_workspace_bytes(pllb_trainer t);
 int64_t pllb_train_kernel_launches(pllb_trainer t);
+/* Steps that ran as a replay of a captured CUDA graph (a batch shape (B, T, mode) runs eagerly
+ * once, is captured on its second occurrence and replayed afterwards; PLLB_TRAIN_GRAPH=0 disables). */
+int64_t pllb_train_graph_replays(pllb_trainer t);
 /* A fresh optimizer: zero moments, step count 0, learning rate lr — the reference
  * re-creates AdamW at the start of every epoch (MLM_PLL/main.py:76). */
 int pllb_train_reset_optimizer(pllb_trainer t, float lr);

@@ -181,6 +181,28 @@ def test_dropout_is_seeded_and_eval_ignores_it(gold_dir):
     assert np.isfinite(lh).all()
 
 
+def test_graph_replay_is_bit_identical_to_eager_launches(gold_dir, monkeypatch):
+    """A batch shape runs eagerly once, is captured as a CUDA graph on its second occurrence and replayed
+    afterwards (dropout seed and Adam bias corrections are read from device memory, so the graph is
+    step-independent).  Same losses and same final weights, bit for bit, as with PLLB_TRAIN_GRAPH=0."""
+    case, sd, rows, _ = _case(gold_dir, "tiny_perturbed")
+    ids, am, lab = _batch(rows[:32])
+    ids2, am2, lab2 = _batch(rows[40:56])
+
+    def run():
+        with engine.MlmTrainer(sd, case["cfg"], lr=1e-3, hidden_dropout=0.1, attention_dropout=0.1, seed=5, max_rows=2048, max_seq=64) as tr:
+            losses = [tr.step(ids, am, lab, mode=1) for _ in range(5)]
+            losses += [tr.step(ids2, am2, lab2, mode=1) for _ in range(3)] + [tr.step(ids, am, lab, mode=0) for _ in range(3)]
+            return losses, tr.state_dict(), tr.graph_replays(), tr.kernel_launches()
+
+    l_graph, s_graph, replays, launches_g = run()
+    monkeypatch.setenv("PLLB_TRAIN_GRAPH", "0")
+    l_eager, s_eager, replays_e, launches_e = run()
+    assert replays == 4 + 2 + 2 and replays_e == 0 and launches_g == launches_e
+    assert l_graph == l_eager and all(bool((s_graph[k] == s_eager[k]).all()) for k in s_graph)
+    assert len(set(l_graph[:5])) == 5                 # a new dropout mask and a new Adam step every replay
+
+
 def test_fine_tuned_checkpoint_is_scored_by_the_scoring_path(gold_dir, tmp_path):
     """task: training through the CLI (MLM_PLL/main.py:117-161 drop-in) -> checkpoint_<epoch>.pth + loss.json;
     the checkpoint is a bare state_dict that the scoring path loads (MLM_PLL/main.py:185-187) and whose PLLs
