@@ -48,20 +48,41 @@ constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_CN = 4;
 
-constexpr int SMEM_XCHG = 2 * 2 * MAX_CN * BM * 8;                         // [parity][rank*2+half][row] float2
+template <int CN>
+constexpr int smem_xchg() { return 2 * 2 * CN * BM * 8; }                 // [parity][rank*2+half][row] float2
 constexpr int SMEM_BARS = 512;
+constexpr int SMEM_LIMIT = 232448;             // 227 KiB of dynamic shared memory per CTA
+// bias | gamma | beta of this CTA's 256 columns, staged once.  The epilogue reads 12 float4 of them per
+// 16-column chunk on its dependent chain; as global loads they compete for the ~28 KB of L1 that
+// 227 KB of shared memory leave with the residual stream passing through (131 KB per tile), so a
+// good part of them are L2 round trips.  From shared memory they cost one fixed short latency.
+constexpr int SMEM_PAR = 3 * BN * 4;
 template <bool STAGED, bool PAIR>
 constexpr int ln_stages() {
   return PAIR ? (STAGED ? 4 : 6) : (STAGED ? 3 : 4);
 }
-template <bool STAGED, bool PAIR>
-constexpr int smem_total() {
+template <int CN, bool STAGED, bool PAIR>
+constexpr int smem_without_params() {
   return ln_stages<STAGED, PAIR>() * (A_STAGE_BYTES + (PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES)) +
-         (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + SMEM_XCHG + SMEM_BARS + 1024;
+         (STAGED ? EPI_WARPS * 2 * BOX_BYTES : 0) + smem_xchg<CN>() + SMEM_BARS + 1024;
+}
+// (the staged single-CTA form at H = 1024 has no 3 KB left: it keeps the global loads)
+template <int CN, bool STAGED, bool PAIR>
+constexpr bool params_in_smem() {
+#ifdef PLLB_LN_PARAMS_GLOBAL
+  return false;                                // A/B builds
+#else
+  return smem_without_params<CN, STAGED, PAIR>() + SMEM_PAR <= SMEM_LIMIT;
+#endif
+}
+template <int CN, bool STAGED, bool PAIR>
+constexpr int smem_total() {
+  return smem_without_params<CN, STAGED, PAIR>() + (params_in_smem<CN, STAGED, PAIR>() ? SMEM_PAR : 0);
 }
 
-static_assert(smem_total<true, false>() <= 232448 && smem_total<false, false>() <= 232448 &&
-              smem_total<true, true>() <= 232448 && smem_total<false, true>() <= 232448, "shared memory budget of one CTA");
+static_assert(smem_total<4, true, false>() <= SMEM_LIMIT && smem_total<4, false, false>() <= SMEM_LIMIT &&
+              smem_total<4, true, true>() <= SMEM_LIMIT && smem_total<4, false, true>() <= SMEM_LIMIT &&
+              smem_total<3, true, false>() <= SMEM_LIMIT, "shared memory budget of one CTA");
 
 struct LnParams {
   int M, K, H;
@@ -150,7 +171,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
   const uint32_t sEpi = smem_base + SMEM_PIPE;
   const uint32_t sXchg = sEpi + SMEM_EPI;
-  const uint32_t sBar = sXchg + SMEM_XCHG;
+  constexpr int SMEM_XCHG = smem_xchg<CN>();
+  constexpr bool PAR_SMEM = params_in_smem<CN, STAGED, PAIR>();
+  const uint32_t sBar = sXchg + SMEM_XCHG + (PAR_SMEM ? SMEM_PAR : 0);
+  float* par_f = reinterpret_cast<float*>(smem_gen + SMEM_PIPE + SMEM_EPI + SMEM_XCHG);      // bias[256] | gamma[256] | beta[256]
+  const float4* par4 = reinterpret_cast<const float4*>(par_f);
   float2* xchg = reinterpret_cast<float2*>(smem_gen + SMEM_PIPE + SMEM_EPI);   // [parity][rank*2+half][row]
   const uint32_t bar_full = sBar;                         // STAGES
   const uint32_t bar_empty = bar_full + 8 * STAGES;       // STAGES
@@ -206,6 +231,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
       tmem_alloc(tmem_slot, TMEM_COLS);
       tmem_relinquish();
+    }
+  }
+  if constexpr (PAR_SMEM) {
+    if (warp >= 2) {                          // the 256 epilogue threads stage one column each
+      const int i = (int)threadIdx.x - 64;
+      par_f[i] = p.bias[n0 + i];
+      par_f[BN + i] = p.gamma[n0 + i];
+      par_f[2 * BN + i] = p.beta[n0 + i];
     }
   }
   tcgen05_fence_before();
@@ -340,7 +373,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_wait_ld();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 b = ldg_f4_ordered(p.bias + n0 + cbase + 16 * j + 4 * c);
+          float4 b;
+          if constexpr (PAR_SMEM) b = par4[(cbase + 16 * j) / 4 + c];
+          else b = ldg_f4_ordered(p.bias + n0 + cbase + 16 * j + 4 * c);
           const float v0 = (__uint_as_float(t[4 * c + 0]) + b.x) + rr[c].x;
           const float v1 = (__uint_as_float(t[4 * c + 1]) + b.y) + rr[c].y;
           const float v2 = (__uint_as_float(t[4 * c + 2]) + b.z) + rr[c].z;
@@ -361,7 +396,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       // ---- exchange (mean, M2) of the 2*CN column groups of every row
       {
-        const uint32_t slot = sXchg + (uint32_t)((xpar * (2 * MAX_CN) + cg * 2 + half) * BM + row_in_tile) * 8;
+        const uint32_t slot = sXchg + (uint32_t)((xpar * (2 * CN) + cg * 2 + half) * BM + row_in_tile) * 8;
         const uint32_t xb = bar_x + 8 * xpar;
         if (ew == 0 && lane == 0) mbar_arrive_expect_tx(xb, CN * EPI_WARPS * 32 * 8);   // this tile's inbox
 #pragma unroll
@@ -378,7 +413,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float2 st[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          st[g] = xchg[(xpar * (2 * MAX_CN) + g) * BM + row_in_tile];
+          st[g] = xchg[(xpar * (2 * CN) + g) * BM + row_in_tile];
           mean += st[g].x;
         }
         mean *= (1.0f / G);
@@ -409,8 +444,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t pk[8];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 g4 = ldg_f4_ordered(p.gamma + n0 + cbase + 16 * j + 4 * c);
-          const float4 b4 = ldg_f4_ordered(p.beta + n0 + cbase + 16 * j + 4 * c);
+          float4 g4, b4;
+          if constexpr (PAR_SMEM) {
+            g4 = par4[(BN + cbase + 16 * j) / 4 + c];
+            b4 = par4[(2 * BN + cbase + 16 * j) / 4 + c];
+          } else {
+            g4 = ldg_f4_ordered(p.gamma + n0 + cbase + 16 * j + 4 * c);
+            b4 = ldg_f4_ordered(p.beta + n0 + cbase + 16 * j + 4 * c);
+          }
           float4 y;
           y.x = fmaf(fmaf(__uint_as_float(t[4 * c + 0]), rstd, nmr), g4.x, b4.x);
           y.y = fmaf(fmaf(__uint_as_float(t[4 * c + 1]), rstd, nmr), g4.y, b4.y);
@@ -477,7 +518,7 @@ template <int CN, int DT, bool STAGED, bool PAIR>
 int launch_cn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& t16,
               const LnParams& lp, int64_t M, cudaStream_t stream) {
   auto kern = gemm_ln_kernel<CN, DT, STAGED, PAIR>;
-  constexpr int SMEM_TOTAL = smem_total<STAGED, PAIR>();
+  constexpr int SMEM_TOTAL = smem_total<CN, STAGED, PAIR>();
   constexpr int CSIZE = PAIR ? 2 * CN : CN;
   PLLB_CUDA(opt_in_smem(kern, SMEM_TOTAL));
   cudaLaunchConfig_t cfg{};
