@@ -93,6 +93,7 @@ struct LnParams {
   const float* beta;
   float eps;
   int amc;                // 1: the A tile is TMA-multicast to the CN CTAs of the cluster (each issues a share of its 32-row boxes)
+  int apf;                // 1: the producer prefetches the NEXT row block's A boxes into L2 while this block is multiplied
 };
 
 template <bool FP16>
@@ -252,6 +253,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t stage = 0, phase = 0;
       for (int mb = cluster; mb < tiles_m; mb += n_clusters) {
         const int m0 = mb * ROWS + (int)rh * BM;
+        // Experiment (PLLB_LN_APF, off by default): request the NEXT row block's A boxes into L2 one
+        // block ahead.  ncu shows the K = H launch waiting 20 % of its epilogue time for the accumulator
+        // (A comes from HBM, 3 stages of 64 columns in flight), but the prefetch made it SLOWER
+        // (attention-output 490 -> 547 ms, FFN2 940 -> 1320 ms in the C2 step): the memory system is
+        // throughput-bound there, extra requests only queue in front of the real loads.
+        if (p.apf && mb + n_clusters < tiles_m) {
+          const int m0n = (mb + n_clusters) * ROWS + (int)rh * BM;
+          const int b0 = amc ? (int)rank : 0, bs = amc ? CN : 1;
+          for (int kb = 0; kb < num_kb; ++kb)
+            for (int b = b0; b < BM / A_BOX_ROWS; b += bs) tma_prefetch_l2_2d(&tmA, kb * BK, m0n + b * A_BOX_ROWS);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if constexpr (PAIR) {
@@ -591,7 +603,10 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, pair ? BN / 2 : BN, BK))) return rc;
   if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
   static const int amc = [] { const char* e = getenv("PLLB_LN_AMC"); return e ? atoi(e) : 1; }();
-  LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps, amc};
+  // PLLB_LN_APF: L2 prefetch of the next row block's A boxes: 0 never (default: measured slower), 1 the K <= H launches, 2 every launch
+  static const int apf_policy = [] { const char* e = getenv("PLLB_LN_APF"); return e ? atoi(e) : 0; }();
+  const int apf = apf_policy == 2 || (apf_policy == 1 && staged) ? 1 : 0;
+  LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps, amc, apf};
 #define PLLB_LN(CN_)                                                                                          \
   case CN_:                                                                                                   \
     switch (dt) {                                                                                             \

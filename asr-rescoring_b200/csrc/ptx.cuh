@@ -81,6 +81,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking): the later
+// cp.async.bulk.tensor load of the same box then pays an L2 hit instead of the HBM latency.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
 // 2-D tile load: coordinates {c0 = innermost (element index), c1 = row}.
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
