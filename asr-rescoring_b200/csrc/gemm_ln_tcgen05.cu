@@ -585,7 +585,9 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
   // epilogue-paced (K <= H): staged 16-bit output; mainloop-paced (K > H): deeper operand ring
-  const bool staged = K <= H;
+  // PLLB_LN_STAGED (experiment knob): 0 / 1 forces the direct / staged form for every launch
+  static const int staged_force = [] { const char* e = getenv("PLLB_LN_STAGED"); return e ? atoi(e) : -1; }();
+  const bool staged = staged_force >= 0 ? staged_force != 0 : K <= H;
   // cta_group::2 pairs inside the LayerNorm cluster (PLLB_LN_PAIR: 0 never, 1 default policy, 2 always,
   // 3 every mainloop-paced launch whatever the hidden size).
   // Default: the mainloop-paced launches (K > H, i.e. FFN2) for H = 256 (cluster 2: 148 SMs), H = 768
@@ -595,8 +597,9 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
   const char* pe = getenv("PLLB_LN_PAIR");
   const int pair_policy = pe ? atoi(pe) : 1;
   const int cn = H / BN;
-  const bool pair = M > 2 * BM && (pair_policy == 2 || (pair_policy == 3 && !staged) ||
-                                   (pair_policy == 1 && !staged && cn != 2));
+  const bool mainloop_paced = K > H;
+  const bool pair = M > 2 * BM && (pair_policy == 2 || (pair_policy == 3 && mainloop_paced) ||
+                                   (pair_policy == 1 && mainloop_paced && cn != 2));
   CUtensorMap ta, tb, t16;
   int rc;
   if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
