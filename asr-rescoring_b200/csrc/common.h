@@ -43,6 +43,15 @@ int sm_count();   // SMs of the current device (cached)
 int get_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elt_bytes, uint64_t rows, uint64_t cols,
                 uint32_t box_rows, uint32_t box_cols);
 
+// K-blocked 16-bit activation [rows, cols] (cols % 64 == 0, buffer padded to a multiple of 32 rows): tiles of
+// 32 rows x 64 columns (4 KB) stored contiguously, tile (rb, cb) at ((rb * cols/64 + cb) * 4096) bytes, so
+// that every TMA box of a GEMM operand / epilogue is ONE contiguous burst instead of 32 pieces of 128 bytes at
+// the row pitch (tools/pitch_probe.cu: 6.2-6.6 against 5.2-5.3 TB/s when streaming).  EXPERIMENT, off by
+// default: inside the FFN2 mainloop the row-major form is faster.  4-D tensor map, coordinates
+// {column in tile, row in tile, column tile, row tile}, box {64, 32, 1, 1}, 128-byte swizzle: the
+// shared-memory image of a box is the one of the 2-D row-major map.
+int get_tmap_blocked(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols);
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (keyed by its address — every
 // instantiation with the same signature has the same pointer TYPE) and device.
 template <typename K>
@@ -89,12 +98,15 @@ struct LseArgs {
 // C[M,N] = A[M,K] * W[N,K]^T (+ epilogue).  A, W bf16 row-major (K contiguous).
 // N % 256 == 0 (pad W rows with zeros), K % 64 == 0.  ldc = N.
 // dt: DT_BF16 or DT_FP16.
+// c_blocked: the 16-bit output C is written in the K-blocked layout (get_tmap_blocked) instead of row-major.
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                        int epilogue, const LseArgs* lse, int dt, cudaStream_t stream);
+                        int epilogue, const LseArgs* lse, int dt, cudaStream_t stream, bool c_blocked = false);
 // hidden_f32 = LayerNorm(A * W^T + bias + hidden_f32) in place, hidden_16 = 16-bit copy
 // (gemm_ln_tcgen05.cu: cluster of H/256 CTAs per 128-row block, row statistics through DSMEM).
+// a_blocked: A is stored in the K-blocked layout.
 int launch_gemm_ln(const void* A, const void* W, const float* bias, const float* gamma, const float* beta, float eps,
-                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, int dt, cudaStream_t stream);
+                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, int dt, cudaStream_t stream,
+                   bool a_blocked = false);
 int launch_gemm_simt(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
                      int epilogue, cudaStream_t stream);
 

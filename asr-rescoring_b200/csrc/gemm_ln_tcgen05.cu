@@ -94,6 +94,7 @@ struct LnParams {
   float eps;
   int amc;                // 1: the A tile is TMA-multicast to the CN CTAs of the cluster (each issues a share of its 32-row boxes)
   int apf;                // 1: the producer prefetches the NEXT row block's A boxes into L2 while this block is multiplied
+  int a_blocked;          // 1: A is stored K-blocked (4-D tensor map: tiles of 32 rows x 64 columns contiguous, common.h)
 };
 
 template <bool FP16>
@@ -258,7 +259,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // (A comes from HBM, 3 stages of 64 columns in flight), but the prefetch made it SLOWER
         // (attention-output 490 -> 547 ms, FFN2 940 -> 1320 ms in the C2 step): the memory system is
         // throughput-bound there, extra requests only queue in front of the real loads.
-        if (p.apf && mb + n_clusters < tiles_m) {
+        if (p.apf && !p.a_blocked && mb + n_clusters < tiles_m) {
           const int m0n = (mb + n_clusters) * ROWS + (int)rh * BM;
           const int b0 = amc ? (int)rank : 0, bs = amc ? CN : 1;
           for (int kb = 0; kb < num_kb; ++kb)
@@ -272,7 +273,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (rh == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (A_STAGE_BYTES + B_BYTES));
 #pragma unroll
             for (int b = 0; b < BM / A_BOX_ROWS; ++b)
-              tma_load_2d_2sm(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, lead_full, kb * BK, m0 + b * A_BOX_ROWS);
+              if (p.a_blocked) tma_load_4d_2sm(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, lead_full, 0, 0, kb, (m0 >> 5) + b);
+              else tma_load_2d_2sm(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, lead_full, kb * BK, m0 + b * A_BOX_ROWS);
             tma_load_2d_2sm(sB + stage * B_BYTES, &tmB, lead_full, kb * BK, n0 + (int)rh * (BN / 2));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
@@ -280,14 +282,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_arrive_expect_tx(bar_full + 8 * stage, A_STAGE_BYTES + B_STAGE_BYTES);
           tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, bar_full + 8 * stage, kb * BK, n0);
           if (amc) {
-            for (int b = (int)rank; b < BM / A_BOX_ROWS; b += CN)
-              tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, kb * BK,
-                                    m0 + b * A_BOX_ROWS, mask_all);
+            for (int b = (int)rank; b < BM / A_BOX_ROWS; b += CN) {
+              if (p.a_blocked)
+                tma_load_4d_multicast(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, 0, 0, kb,
+                                      (m0 >> 5) + b, mask_all);
+              else
+                tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, kb * BK,
+                                      m0 + b * A_BOX_ROWS, mask_all);
+            }
           } else {
 #pragma unroll
-            for (int b = 0; b < BM / A_BOX_ROWS; ++b)
-              tma_load_2d(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, kb * BK,
-                          m0 + b * A_BOX_ROWS);
+            for (int b = 0; b < BM / A_BOX_ROWS; ++b) {
+              if (p.a_blocked)
+                tma_load_4d(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, 0, 0, kb, (m0 >> 5) + b);
+              else
+                tma_load_2d(sA + stage * A_STAGE_BYTES + b * A_BOX_BYTES, &tmA, bar_full + 8 * stage, kb * BK,
+                            m0 + b * A_BOX_ROWS);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -580,7 +591,8 @@ int launch_cn_dt(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 }  // namespace
 
 int launch_gemm_ln(const void* A, const void* W, const float* bias, const float* gamma, const float* beta, float eps,
-                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, int dt, cudaStream_t stream) {
+                   float* hidden_f32, void* hidden_16, int64_t M, int H, int K, int dt, cudaStream_t stream,
+                   bool a_blocked) {
   if (M <= 0) return PLLB_OK;
   if (H % BN != 0 || H / BN > MAX_CN || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm_ln: need H in {256,512,768,1024} and K % 64 == 0");
@@ -602,14 +614,16 @@ int launch_gemm_ln(const void* A, const void* W, const float* bias, const float*
                                    (pair_policy == 1 && mainloop_paced && cn != 2));
   CUtensorMap ta, tb, t16;
   int rc;
-  if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
+  if (a_blocked) {
+    if ((rc = get_tmap_blocked(&ta, A, (uint64_t)M, (uint64_t)K))) return rc;
+  } else if ((rc = tmap2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)K, 32, BK))) return rc;   // 32-row boxes
   if ((rc = tmap2d(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)H, (uint64_t)K, pair ? BN / 2 : BN, BK))) return rc;
   if ((rc = tmap2d(&t16, hidden_16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)H, 32, 64))) return rc;
   static const int amc = [] { const char* e = getenv("PLLB_LN_AMC"); return e ? atoi(e) : 1; }();
   // PLLB_LN_APF: L2 prefetch of the next row block's A boxes: 0 never (default: measured slower), 1 the K <= H launches, 2 every launch
   static const int apf_policy = [] { const char* e = getenv("PLLB_LN_APF"); return e ? atoi(e) : 0; }();
   const int apf = apf_policy == 2 || (apf_policy == 1 && staged) ? 1 : 0;
-  LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps, amc, apf};
+  LnParams lp{(int)M, K, H, hidden_f32, reinterpret_cast<__nv_bfloat16*>(hidden_16), bias, gamma, beta, eps, amc, apf, a_blocked ? 1 : 0};
 #define PLLB_LN(CN_)                                                                                          \
   case CN_:                                                                                                   \
     switch (dt) {                                                                                             \

@@ -60,6 +60,7 @@ struct KParams {
   const float* bias;
   LseArgs lse;
   int early_release;
+  int c_blocked;          // the 16-bit output goes out in the K-blocked layout (4-D tensor map, common.h)
 };
 
 // HF activations "gelu" = nn.functional.gelu (erf form): 0.5 x (1 + erf(x / sqrt 2)).
@@ -354,7 +355,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, buf, n0 + c0, m0 + q * 32);
+            if (p.c_blocked) tma_store_4d(&tmC, buf, 0, 0, (n0 + c0) >> 6, (m0 + q * 32) >> 5);
+            else tma_store_2d(&tmC, buf, n0 + c0, m0 + q * 32);
             tma_store_commit();
           }
         }
@@ -483,7 +485,7 @@ int pair_mode(int epilogue) {
 }  // namespace
 
 int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C, int64_t M, int N, int K,
-                        int epilogue, const LseArgs* lse, int dt, cudaStream_t stream) {
+                        int epilogue, const LseArgs* lse, int dt, cudaStream_t stream, bool c_blocked) {
   if (M <= 0) return PLLB_OK;
   if (N % BN != 0 || K % BK != 0 || M > INT32_MAX)
     return fail(PLLB_ERR_INVALID, "gemm: need N % 256 == 0 and K % 64 == 0");
@@ -494,13 +496,17 @@ int launch_gemm_tcgen05(const void* A, const void* W, const float* bias, void* C
   const bool mc = mode != 0;
   if ((rc = make_tmap(&tb, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, mc ? BN / 2 : BN, BK))) return rc;
   tc = ta;
-  if (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16) {
+  if (c_blocked && epilogue != EPI_BIAS_BF16 && epilogue != EPI_BIAS_GELU_BF16)
+    return fail(PLLB_ERR_INVALID, "gemm: the K-blocked output layout exists for the 16-bit epilogues only");
+  if (c_blocked) {
+    if ((rc = get_tmap_blocked(&tc, C, (uint64_t)M, (uint64_t)N))) return rc;
+  } else if (epilogue == EPI_BIAS_BF16 || epilogue == EPI_BIAS_GELU_BF16) {
     if ((rc = make_tmap(&tc, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)M, (uint64_t)N, 32, 64))) return rc;
   } else if (epilogue == EPI_BIAS_F32 || epilogue == EPI_BIAS_GELU_F32) {
     if ((rc = make_tmap(&tc, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)N, 32, 32))) return rc;
   }
   KParams kp{};
-  kp.M = (int)M; kp.N = N; kp.K = K; kp.bias = bias;
+  kp.M = (int)M; kp.N = N; kp.K = K; kp.bias = bias; kp.c_blocked = c_blocked ? 1 : 0;
   { const char* e = getenv("PLLB_GEMM_EARLY_RELEASE"); kp.early_release = e ? atoi(e) : 1; }
   if (epilogue == EPI_LSE) {
     if (!lse) return fail(PLLB_ERR_INVALID, "gemm: LSE epilogue needs LseArgs");

@@ -97,6 +97,28 @@ def test_bert_base_shape_two_layers_vs_oracle():
     print(f"bert-base shape, 2 layers: loss {loss:.5f} (oracle {o_loss:.5f}), worst gradient rel L2 error {worst:.4f}")
 
 
+def test_bert_base_twelve_layers_three_steps_vs_oracle():
+    """The shape and depth the reference fine-tunes (bert-base-chinese, train.yaml:23-24), three AdamW steps at
+    lr 1e-4 on batches of 32 rows: the batch losses follow the fp32 autograd oracle within 0.02 nats, and the
+    loss falls."""
+    cfg = synth.BERT_BASE_CHINESE
+    sd = synth.random_init_state_dict(cfg, 10)
+    nb = synth.make_nbest(8, 1, seed=11)
+    tok, off = nb.packed_tokens()
+    rows = train_oracle.training_rows([[int(t) for t in tok[off[i]:off[i + 1]]] for i in range(len(off) - 1)])
+    assert len(rows) >= 96
+    params = train_oracle.parameters(sd)
+    o_losses = []
+    train_oracle.run_one_epoch(params, cfg, rows[:96], 32, 1e-4, True, batch_losses=o_losses)
+    got = []
+    with engine.MlmTrainer(sd, cfg, lr=1e-4, hidden_dropout=0.0, attention_dropout=0.0, max_rows=32 * 40, max_seq=40) as tr:
+        tr.reset_optimizer(1e-4)
+        for s0 in (0, 32, 64):
+            got.append(tr.step(*_batch(rows[s0:s0 + 32]), mode=1))
+    print(f"bert-base-chinese, 12 layers: device losses {[round(x, 4) for x in got]}, oracle {[round(x, 4) for x in o_losses]}")
+    assert all(abs(a - b) <= 0.02 for a, b in zip(got, o_losses)) and got[2] < got[0]
+
+
 def test_adamw_update_matches_torch_given_the_same_gradients(gold_dir):
     """The optimizer in isolation: gradients of a mode-2 pass, then a mode-1 pass on the same batch
     (same gradients: no dropout, deterministic kernels); torch.optim.AdamW on CPU fed with the

@@ -52,7 +52,7 @@ def main():
            "| file | workload | GPUs | dtype | value hyps/s | ms/step | e2e hyps/s | roofline (dominant kernel) frac | GEMM family frac | CPU reference arm hyps/s | clocks |",
            "|---|---|---|---|---|---|---|---|---|---|---|"]
     for f in sorted(os.listdir(P)):
-        if f.startswith("r02_bench_") and f.endswith(".json") and "reference_arm" not in f:
+        if (f.startswith("r02_bench_") or f.startswith("r02_final_bench_")) and f.endswith(".json") and "reference_arm" not in f:
             out.append(bench_row(f))
     out += ["", "## Launch list — default kernels (`r02_launches.csv`)\n", sp.launches(os.path.join(P, "r02_launches.csv")), "",
             "## One encoder layer, `--set full` (`r02_ncu_full_layer.csv`; M = 999 k rows)\n",
@@ -64,6 +64,12 @@ def main():
             "## Opt-in TMA-fed attention kernel (`PLLB_ATT_TMA=1`)\n",
             sp.launches(os.path.join(P, "r02_launches_att_tma.csv")), "",
             raw_table(os.path.join(P, "r02_ncu_full_layer_att_tma.csv"), only="attention"), ""]
+    fin = os.path.join(P, "r02_final_launches.csv")
+    if os.path.exists(fin):
+        out += ["## Launch list of the final build (`r02_final_launches.csv`, same command)\n", sp.launches(fin), ""]
+    ln = os.path.join(P, "r02_ncu_full_gemm_ln_after_smem_params.md")
+    if os.path.exists(ln):
+        out += ["## Fused GEMM + LayerNorm kernels after the shared-memory parameters, `--set full`\n", open(ln).read(), ""]
     extra = os.path.join(P, "r02_notes.md")
     if os.path.exists(extra):
         out.append(open(extra).read())
