@@ -130,9 +130,11 @@ def _iter_rows(dataloader) -> Iterable[dict]:
                 yield row
 
 
-def _run_loss_epoch(config, model: MlmTrainer, dataloader, train_mode: bool) -> float:
-    """run_one_epoch with do_scoring=False (MLM_PLL/main.py:73-99,109-112): the mean of the batch
-    losses; train_mode adds backward + AdamW per batch, with a fresh optimizer per epoch (:76)."""
+def _run_loss_epoch(config, model: MlmTrainer, dataloader, train_mode: bool, output_score=None, do_scoring=False):
+    """run_one_epoch on a trainer (MLM_PLL/main.py:73-114): the mean of the batch losses; train_mode adds
+    backward + AdamW per batch, with a fresh optimizer per epoch (:76).  do_scoring additionally adds, for
+    every row, log_softmax(logits[mask_pos])[labels[mask_pos]] of THIS forward pass (dropout active when
+    train_mode, as in the reference) to output_score and returns it instead of the loss (:100-107,111-114)."""
     if not isinstance(model, MlmTrainer):
         raise TypeError("the training / loss pass needs an engine.MlmTrainer (build_trainer), not a PllScorer")
     if train_mode:
@@ -142,6 +144,13 @@ def _run_loss_epoch(config, model: MlmTrainer, dataloader, train_mode: bool) -> 
         ids, am, lab = pad_batch(batch)
         epoch_loss += model.step(ids, am, lab, mode=1 if train_mode else 0)
         n_batches += 1
+        if do_scoring:
+            T = ids.shape[1]
+            nll = model.row_losses(ids.size)
+            for b, row in enumerate(batch):
+                output_score[row["utt_id"]][row["hyp_id"]] += float(-nll[b * T + int(row["mask_pos"])])
+    if do_scoring:
+        return output_score
     return epoch_loss / len(dataloader) if n_batches else 0.0
 
 
@@ -152,11 +161,9 @@ def run_one_epoch(config, model, dataloader, output_score=None, train_mode=True,
     Rows of one hypothesis are consecutive (preprocess.py emits them so); a row list cut in
     the middle of a hypothesis by ``num_of_data`` adds only the rows present, like the
     reference."""
-    if not do_scoring:
-        return _run_loss_epoch(config, model, dataloader, train_mode)
-    if train_mode:
-        raise NotImplementedError("scoring while training (train_mode and do_scoring both set) is never used by the "
-                                  "reference's drivers (MLM_PLL/main.py:135-153,194-201) and is not implemented")
+    if not do_scoring or train_mode or isinstance(model, MlmTrainer):
+        # (scoring while training, and scoring through a trainer, go row by row through the padded-batch forward)
+        return _run_loss_epoch(config, model, dataloader, train_mode, output_score, do_scoring)
     groups: List[Tuple[str, str, List[int], List[int]]] = []   # utt, hyp, tokens, mask positions present
     last_key = None
     for row in _iter_rows(dataloader):

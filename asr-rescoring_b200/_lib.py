@@ -86,6 +86,7 @@ SIGNATURES = {
     "pllb_train_graph_replays": (c_int64, [c_void_p]),
     "pllb_train_reset_optimizer": (c_int, [c_void_p, c_float]),
     "pllb_train_step_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_float)]),
+    "pllb_train_row_losses_host": (c_int, [c_void_p, c_void_p, c_int32]),
     "pllb_train_export": (c_int, [c_void_p, POINTER(Weights)]),
     "pllb_train_export_grads": (c_int, [c_void_p, POINTER(Weights)]),
 }

@@ -69,6 +69,7 @@ struct pllb_trainer_ctx {
   int64_t step = 0;        // optimizer steps since the last reset (Adam bias correction)
   int64_t calls = 0;       // forward passes since create (dropout stream)
   int64_t launches = 0;
+  int last_rows = 0;       // B * T of the last step (pllb_train_row_losses_host)
   // per-step scalars (device copy read by the kernels; pinned host copy filled before every step)
   TrainStepParams* params_dev = nullptr;
   TrainStepParams* params_host = nullptr;
@@ -531,7 +532,16 @@ int pllb_train_step_host(pllb_trainer c, const int32_t* input_ids, const int32_t
   PLLB_CUDA(cudaMemcpyAsync(c->n_valid, c->host_stage + 2 * R, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
   float loss = 0.f;
   RC(step_impl(c, B, T, mode, &loss, s));
+  c->last_rows = R;
   if (out_loss) *out_loss = loss;
+  return PLLB_OK;
+}
+
+int pllb_train_row_losses_host(pllb_trainer c, float* out, int32_t n) {
+  if (!c || !out || n < 0 || n > c->last_rows) return fail(PLLB_ERR_INVALID, "pllb_train_row_losses_host: bad argument (n exceeds the rows of the last step)");
+  PLLB_CUDA(cudaSetDevice(c->device));
+  PLLB_CUDA(cudaMemcpyAsync(out, c->loss_rows, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  PLLB_CUDA(cudaStreamSynchronize(c->stream));
   return PLLB_OK;
 }
 

@@ -324,6 +324,12 @@ class MlmTrainer:
                                              int(mode), ctypes.byref(loss)))
         return float(loss.value)
 
+    def row_losses(self, n_rows: int) -> np.ndarray:
+        """-log_softmax(logits)[labels] of every position of the last step (float32 [B*T], row-major)."""
+        out = np.zeros(int(n_rows), np.float32)
+        check(self._lib.pllb_train_row_losses_host(self._h, _np_ptr(out), int(n_rows)))
+        return out
+
     def _export(self, fn) -> Dict[str, "torch.Tensor"]:
         import torch
         bufs = {}

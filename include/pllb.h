@@ -282,6 +282,11 @@ int pllb_train_reset_optimizer(pllb_trainer t, float lr);
  * out_loss: the batch loss (output.loss.item(), MLM_PLL/main.py:109).  Synchronises. */
 int pllb_train_step_host(pllb_trainer t, const int32_t* input_ids, const int32_t* n_valid,
                          const int32_t* labels, int32_t B, int32_t T, int32_t mode, float* out_loss);
+/* Per-position losses of the last step, HOST float[B*T]: loss[b*T + t] = -log_softmax(logits[b, t])[labels[b, t]].
+ * With the for_scoring rows of preprocess.py (labels = the unmasked sequence) the entry at the row's mask_pos is
+ * minus the PLL term the scoring branch adds (MLM_PLL/main.py:101-107) — this is what makes
+ * run_one_epoch(train_mode=..., do_scoring=True) work on a trainer. */
+int pllb_train_row_losses_host(pllb_trainer t, float* out, int32_t n);
 /* Writes the fp32 master weights (model.state_dict(), MLM_PLL/main.py:155) / the gradients of
  * the last mode-1/2 step into the caller's DEVICE tensors; a NULL pointer skips that tensor;
  * q/k/v are un-stacked; decoder_w is written only if it is not the word_emb pointer. */

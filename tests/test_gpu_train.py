@@ -275,6 +275,31 @@ resume:
     assert worst <= 0.05 and moved > 0.2
 
 
+def test_scoring_through_the_trainer_matches_the_scoring_path(gold_dir):
+    """run_one_epoch(do_scoring=True) on a trainer — the padded-batch forward of the training path, row by row as
+    the reference does it (MLM_PLL/main.py:100-107) — gives the PLLs of the varlen scoring path and of the oracle;
+    with train_mode=True as well (dropout 0) the scores are those of the weights BEFORE each batch's update."""
+    import importlib
+    m = importlib.import_module("asr_rescoring_b200.MLM_PLL.main")
+    case, sd, _, _ = _case(gold_dir, "tiny_lr1e-5")
+    hyps = {"u1": {"hyp_1": case["dev_tokens"][0], "hyp_2": case["dev_tokens"][1]}, "u2": {"hyp_1": case["dev_tokens"][2]}}
+    rows = [r for u, hs in hyps.items() for h, t in hs.items() for r in pll_oracle.expand_rows(t, u, h)]
+    skel = lambda: {u: {h: 0 for h in hs} for u, hs in hyps.items()}
+    exp = pll_oracle.score_hyps(sd, case["cfg"], hyps)
+    conf = SimpleNamespace(lr=1e-5, device="cuda:0")
+    loader = m.set_dataloader(SimpleNamespace(shuffle=False, batch_size=32, num_worker=0), m.MyDataset(rows), True)
+    longest = max(len(r["input_ids"]) for r in rows)
+    with engine.MlmTrainer(sd, case["cfg"], lr=1e-5, hidden_dropout=0.0, attention_dropout=0.0, max_rows=32 * longest, max_seq=longest) as tr:
+        got = m.run_one_epoch(config=conf, model=tr, dataloader=loader, output_score=skel(), train_mode=False, do_scoring=True)
+        got_tr = m.run_one_epoch(config=conf, model=tr, dataloader=loader, output_score=skel(), train_mode=True, do_scoring=True)
+    with engine.PllScorer(sd, case["cfg"]) as sc:
+        fast = sc.score_hyps(hyps)
+    for u in hyps:
+        for h in hyps[u]:
+            assert abs(got[u][h] - exp[u][h]) <= 0.05 and abs(got[u][h] - fast[u][h]) <= 0.05, (u, h, got[u][h], exp[u][h], fast[u][h])
+            assert abs(got_tr[u][h] - exp[u][h]) <= 0.3          # lr 1e-5: the weights move a little between batches
+
+
 def test_training_argument_errors(gold_dir):
     case, sd, rows, _ = _case(gold_dir, "tiny_lr1e-5")
     ids, am, lab = _batch(rows[:8])

@@ -109,8 +109,8 @@ def test_drop_in_function_surface():
     assert m.skeleton_from_rows(rows) == {"u": {"hyp_1": 0, "hyp_2": 0}, "v": {"hyp_1": 0}}
     with pytest.raises(KeyError):            # quirk 3: no hyp_1 row for an utterance
         m.skeleton_from_rows([{"utt_id": "w", "hyp_id": "hyp_2"}])
-    with pytest.raises(NotImplementedError):      # train_mode + do_scoring: never used by the reference's drivers
-        m.run_one_epoch(None, None, [], {}, train_mode=True, do_scoring=True)
+    with pytest.raises(TypeError):                # train_mode needs a trainer, with or without do_scoring
+        m.run_one_epoch(None, object(), [], {}, train_mode=True, do_scoring=True)
     with pytest.raises(TypeError):                # the loss / training pass needs a trainer, not a scorer
         m.run_one_epoch(None, object(), [], None, train_mode=True, do_scoring=False)
 
