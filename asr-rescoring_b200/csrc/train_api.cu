@@ -318,6 +318,13 @@ int step_impl(pllb_trainer_ctx* c, int B, int T, int mode, float* out_loss_host,
     c->launches += ge->launches;
     c->graph_replays += 1;
   } else if (ge && ge->seen >= 1) {
+    if (c->graphs.size() > 256) {              // bound the cache (a caller that never repeats a shape): start over
+      for (auto& kv : c->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      c->graphs.clear();
+      ge = &c->graphs[key];
+      ge->seen = 1;
+    }
     const int64_t before = g_launch_counter;
     PLLB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     const int rc = enqueue_step(c, B, T, mode, s);
