@@ -36,21 +36,27 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     import torch
+    import importlib
     from asr_rescoring_b200 import engine, synth
-    from oracle import pll_oracle, train_oracle
+    from asr_rescoring_b200.synth import CLS_ID, MASK_ID, SEP_ID
     import bench
+    drop_in = importlib.import_module("asr_rescoring_b200.MLM_PLL.main")
+
+    def rows_of(tokens, utt):          # the for_training rows of MLM_PLL/preprocess.py:9-30 (token ids instead of text)
+        return [{"utt_id": utt, "hyp_id": None, "input_ids": [CLS_ID] + tokens[:m] + [MASK_ID] + tokens[m + 1:] + [SEP_ID],
+                 "attention_masks": [1] * (len(tokens) + 2), "mask_pos": m + 1, "labels": [CLS_ID] + tokens + [SEP_ID]}
+                for m in range(len(tokens))]
     cfg = dict(synth.BERT_BASE_CHINESE, num_layers=args.layers)
     sd = synth.random_init_state_dict(cfg, 10)
     need = (args.steps + args.warmup) * args.batch
     nb = synth.make_nbest(max(need // 10, 8), 1, seed=0)
     tok, off = nb.packed_tokens()
-    rows = train_oracle.training_rows([[int(t) for t in tok[off[i]:off[i + 1]]] for i in range(len(off) - 1)])
+    rows = [r for i in range(len(off) - 1) for r in rows_of([int(t) for t in tok[off[i]:off[i + 1]]], f"utt{i}")]
     assert len(rows) >= need, (len(rows), need)
     batches = [rows[i * args.batch:(i + 1) * args.batch] for i in range(args.steps + args.warmup)]
     arrays = []
     for b in batches:
-        ids, am, lab, *_ = pll_oracle.collate(b)
-        arrays.append(tuple(x.numpy().astype(np.int32) for x in (ids, am, lab)))
+        arrays.append(drop_in.pad_batch(b))
     max_rows = max(a[0].size for a in arrays)
     max_seq = max(a[0].shape[1] for a in arrays)
     H, I, V, NL = cfg["hidden"], cfg["intermediate"], cfg["vocab"], cfg["num_layers"]
