@@ -75,11 +75,13 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         launches = (tr.kernel_launches() - l0) / args.steps
+        replays = tr.graph_replays()
         ws = int(tr._lib.pllb_train_workspace_bytes(tr._h))
     tokens = sum(a[0].size for a in arrays[args.warmup:])
     gpu = dict(rows_per_s=args.steps * args.batch / dt, ms_per_step=1e3 * dt / args.steps, row_tokens_per_step=tokens / args.steps,
                tflops=flops_per_row_token * tokens / dt / 1e12, launches_per_step=launches, first_loss=losses[0], last_loss=losses[-1],
-               workspace_gb=ws / 1e9)
+               workspace_gb=ws / 1e9, graph_replays_of_all_steps=f"{replays} of {args.steps + args.warmup}",
+               distinct_batch_shapes=len({a[0].shape for a in arrays}))
     cpu = None
     if args.cpu_batches > 0:
         ref_main = bench._load_reference_module("ref_mlm_pll_main", os.path.join("MLM_PLL", "main.py"), "MLM_PLL")
